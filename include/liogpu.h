@@ -1,0 +1,171 @@
+/*
+ * liogpu.h — C ABI of libliogpu.so: B200-native (sm_100a) scan-to-map registration for liorf.
+ *
+ * This is the drop-in boundary for ONE hot path of JiLiBIT/LIO-SLAM (liorf): every entry point
+ * replaces the body of a member function of the reference's two ROS node classes.  Citations are
+ * relative to the reference tree:
+ *     MO = src/liorf/src/mapOptmization.cpp      IP = src/liorf/src/imageProjection.cpp
+ *     UT = src/liorf/include/utility.h
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - Every call returns an int status: 0 = OK, < 0 = error (nothing written), > 0 = warning
+ *     (the call completed with the reference's own guard behaviour, see LIOGPU_W_*).
+ *   - Point clouds are arrays of records `stride` bytes apart with float x@0, y@4, z@8 and the
+ *     intensity at byte 16 when stride >= 32 (the pcl::PointXYZI layout the reference uses, UT:65)
+ *     or at byte 12 when stride == 16 (packed float4).  Outputs use the same rule.
+ *   - Pointers may be HOST pointers (pageable or pinned) or DEVICE pointers of ctx's GPU; the
+ *     library detects which (cudaPointerGetAttributes).  The caller owns them; the library never
+ *     keeps a caller pointer after the call returns.
+ *   - pose6 = float[6] = {roll, pitch, yaw, x, y, z}: the layout of transformTobeMapped (MO:171).
+ *   - One context = one GPU = one CUDA stream; calls on one context must be serialised by the
+ *     caller (the reference holds `mtx` around the whole path, MO:449).
+ *   - There is no CPU fallback: every entry point fails with LIOGPU_E_CUDA if no sm_100 device
+ *     can be used.
+ */
+#ifndef LIOGPU_H_
+#define LIOGPU_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIOGPU_ABI_VERSION 1
+
+/* status codes */
+#define LIOGPU_OK 0
+#define LIOGPU_E_INVALID (-1)      /* bad argument                                         */
+#define LIOGPU_E_CUDA (-2)         /* CUDA runtime error, see liogpu_last_error            */
+#define LIOGPU_E_NO_MAP (-3)       /* scan2map / knn before any local map was installed    */
+#define LIOGPU_E_NO_KEYFRAME (-4)  /* build_local_map names an id never put                */
+#define LIOGPU_E_CAPACITY (-5)     /* caller's output buffer too small (n_out = needed)    */
+#define LIOGPU_W_LEAF_OVERFLOW 1   /* VoxelGrid index overflow guard: output == input      */
+#define LIOGPU_W_FEW_FEATURES 2    /* n <= 30 scan points: pose untouched (MO:1844,1863)   */
+#define LIOGPU_W_NO_KEYFRAMES 3    /* local map empty: pose untouched (MO:1841)            */
+
+typedef struct liogpu_ctx liogpu_ctx;
+
+/* Parameters the hot path reads from ParamServer (UT:199-331); defaults are UT's compiled-in ones.
+ * Fill with liogpu_default_params() and override. */
+typedef struct liogpu_params {
+  int device;                /* CUDA device ordinal                                              */
+  int n_scan;                /* N_SCAN        (UT:275)  ring bound in deskew (IP:602)            */
+  int horizon_scan;          /* Horizon_SCAN  (UT:276)  n_scan*horizon_scan = scratch hint MO:333 */
+  float mapping_surf_leaf_size;              /* mappingSurfLeafSize            (UT:303, MO:286)  */
+  float surrounding_keyframe_map_leaf_size;  /* surroundingKeyframeMapLeafSize (UT:304, MO:287)  */
+  int downsample_rate;       /* downsampleRate   (UT:277, IP:605)                                */
+  int point_filter_num;      /* point_filter_num (UT:278, IP:608)                                */
+  float lidar_min_front, lidar_min_back, lidar_min_left, lidar_min_right; /* UT:280-283, IP:596  */
+  float lidar_max_range;     /* UT:284, IP:598                                                   */
+  float lidar_max_intensity; /* UT:285, IP:598                                                   */
+  float knn_cell_size;       /* edge of the sorted-grid cell used for the 5-NN index; 0 = auto   */
+  int reserved[7];
+} liogpu_params;
+
+/* Result block of liogpu_scan2map (everything the reference keeps in members after the loop). */
+#define LIOGPU_MAX_ITER 30 /* MO:1848 */
+typedef struct liogpu_s2m_info {
+  int iterations;    /* LM iterations executed (MO:1848-1859)                                      */
+  int converged;     /* 1 if LMOptimization returned true (MO:1833)                                */
+  int n_query;       /* laserCloudSurfLastDSNum                                                    */
+  int n_sel;         /* laserCloudSelNum of the last executed iteration (MO:1721)                  */
+  int is_degenerate; /* isDegenerate after the loop (MO:176)                                       */
+  int tie_queries;   /* last iteration: accepted queries whose 5-NN set contains / borders an
+                        equidistant tie (neighbour parity is "modulo logged ties")                 */
+  float delta_r_deg; /* last iteration's deltaR (MO:1824)                                          */
+  float delta_t_cm;  /* last iteration's deltaT (MO:1828)                                          */
+  double JtJ[36];    /* last iteration's AtA, f64 accumulation before rounding to f32 (MO:1782)    */
+  double Jtr[6];     /* last iteration's AtB (MO:1783)                                             */
+  float pose_hist[LIOGPU_MAX_ITER][6]; /* transformTobeMapped after each executed iteration        */
+  int nsel_hist[LIOGPU_MAX_ITER];
+  float gpu_ms;      /* device time of the loop (CUDA events on the context's stream)              */
+} liogpu_s2m_info;
+
+int liogpu_abi_version(void);
+void liogpu_default_params(liogpu_params* p);
+
+/* allocateMemory (MO:316-349): one context per mapOptimization / ImageProjection instance. */
+int liogpu_create(liogpu_ctx** out, const liogpu_params* params);
+void liogpu_destroy(liogpu_ctx* ctx);
+const char* liogpu_last_error(const liogpu_ctx* ctx);
+
+/* Pinned host memory for callers that want their clouds DMA-able (optional). */
+void* liogpu_host_alloc(unsigned long long bytes);
+void liogpu_host_free(void* p);
+
+/* ImageProjection::projectPointCloud + deskewPoint + findRotation (IP:577-615, 545-575, 502-527).
+ * xyzirt: n records, `stride` bytes apart: x@0 y@4 z@8 intensity@16 ring(u16)@20 time(f32)@24
+ * (PointXYZIRT, IP:4-15).  imu_time/rot_x/rot_y/rot_z: the imuTime/imuRotX/Y/Z tables built by
+ * imuDeskewInfo (IP:359-418) with n_imu = imuPointerCur + 1 valid rows (host code, stays host).
+ * deskew_enabled = (deskewFlag != -1 && cloudInfo.imuAvailable) (IP:547).
+ * Survivors are written in input order to xyzi_out (capacity cap_out records). */
+int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double time_scan_cur,
+                  const double* imu_time, const double* imu_rot_x, const double* imu_rot_y,
+                  const double* imu_rot_z, int n_imu, int deskew_enabled, void* xyzi_out,
+                  int out_stride, int cap_out, int* n_out);
+
+/* mapOptimization::transformPointCloud (MO:849-868). pose6 = keyframe {roll,pitch,yaw,x,y,z}. */
+int liogpu_transform_cloud(liogpu_ctx* ctx, const void* xyzi, int n, int stride,
+                           const float pose6[6], void* xyzi_out, int out_stride);
+
+/* pcl::VoxelGrid<PointXYZI>::filter as called at MO:1536, 1582, 1609 (semantics: SURVEY A.1).
+ * On the overflow guard the input is returned unchanged with LIOGPU_W_LEAF_OVERFLOW. */
+int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride, float leaf,
+                            void* xyzi_out, int out_stride, int cap_out, int* n_out);
+
+/* surfCloudKeyFrames.push_back (MO:2142): keep a lidar-frame keyframe cloud resident on the GPU. */
+int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int stride);
+/* drop all keyframes (node reset). */
+int liogpu_keyframe_clear(liogpu_ctx* ctx);
+int liogpu_keyframe_count(const liogpu_ctx* ctx);
+
+/* extractCloud (MO:1556-1588): transform the k named keyframes by their poses, concatenate in the
+ * given order, VoxelGrid with `leaf`, install the result as the local map and build its 5-NN grid
+ * index.  The host still chooses WHICH keyframes (extractNearby MO:1519-1554 stays host).
+ * xyzi_out may be NULL; otherwise the voxelised map (laserCloudSurfFromMapDS) is copied out. */
+int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k,
+                           float leaf, int* n_map, void* xyzi_out, int out_stride, int cap_out);
+
+/* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
+ * install the cloud as the local map and build the grid index. */
+int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);
+int liogpu_local_map_size(const liogpu_ctx* ctx);
+
+/* The loop of scan2MapOptimization (MO:1848-1859): per iteration surfOptimization (MO:1618-1687),
+ * combineOptimizationCoeffs (MO:1689-1700) and LMOptimization (MO:1702-1837), entirely on device.
+ * scan_ds = laserCloudSurfLastDS (n points).  pose_io = transformTobeMapped, matP_io = matP
+ * (row-major 6x6, MO:177) and degenerate_io = isDegenerate (MO:176) persist across scans in the
+ * reference, so they are in/out.  max_iter <= LIOGPU_MAX_ITER (the reference uses 30).
+ * transformUpdate (MO:1861) stays on the host. */
+int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6],
+                    float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info);
+
+/* downsampleCurrentScan (MO:1605-1611) fused with liogpu_scan2map: the deskewed scan is
+ * voxelised with params.mapping_surf_leaf_size on device and registered without leaving HBM.
+ * n_ds receives laserCloudSurfLastDSNum; scan_ds_out may be NULL. */
+int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int stride,
+                               float pose_io[6], float matP_io[36], int* degenerate_io,
+                               int max_iter, liogpu_s2m_info* info, int* n_ds, void* scan_ds_out,
+                               int out_stride, int cap_out);
+
+/* One surfOptimization pass (MO:1618-1687) with its per-point results exposed for parity checks:
+ * nn_idx[n*5] (indices into the installed local map, ascending distance, -1 when the query has
+ * fewer than 5 map points within the gate), nn_d2[n*5] (pointSearchSqDis), coeff[n*4]
+ * (coeffSelSurfVec: x,y,z,intensity), flag[n] (laserCloudOriSurfFlag), tie[n] (1 = tie logged).
+ * Exactly one of pose6 / T12 (row-major 3x4 transPointAssociateToMap, MO:1615) is non-NULL.
+ * Any output pointer may be NULL. */
+int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int stride,
+                             const float* pose6, const float* T12, int* nn_idx, float* nn_d2,
+                             float* coeff, unsigned char* flag, unsigned char* tie);
+
+/* Timing hook for bench.py: device milliseconds of the last call's kernels (events on ctx's stream). */
+float liogpu_last_gpu_ms(const liogpu_ctx* ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+unsigned long long liogpu_launch_count(const liogpu_ctx* ctx);
+/* The context's cudaStream_t, so a caller timing with CUDA events can record on it. */
+void* liogpu_stream(const liogpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIOGPU_H_ */

@@ -1,0 +1,443 @@
+// api.cu — the C ABI of libliogpu.so (include/liogpu.h).  Thin: argument checks, host<->device
+// staging, and calls into the kernel drivers.  No CPU implementation of any operator lives here:
+// without a usable CUDA device every entry point fails with LIOGPU_E_CUDA.
+#include "common.cuh"
+
+#include <cstring>
+#include <new>
+
+using namespace liogpu;
+
+struct liogpu_ctx {
+  Ctx c;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+bool stride_ok(int stride) { return stride == 16 || (stride >= 32 && (stride % 4) == 0); }
+
+// caller cloud (host or device, `stride` bytes per record) -> packed float4 in dst
+int load_cloud(Ctx* c, const void* src, int n, int stride, DevBuf& dst) {
+  if (n < 0 || (n > 0 && !src) || !stride_ok(stride)) { c->err = "bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
+  LIOGPU_CUDA_OK(c, dst.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4)));
+  if (n == 0) return LIOGPU_OK;
+  const bool dev = is_device_ptr(src);
+  if (stride == 16) {
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst.p, src, (size_t)n * 16, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    return LIOGPU_OK;
+  }
+  const void* d_raw = src;
+  if (!dev) {
+    LIOGPU_CUDA_OK(c, c->raw_in.reserve((size_t)n * stride));
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(c->raw_in.p, src, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    d_raw = c->raw_in.p;
+  }
+  LIOGPU_CUDA_OK(c, launch_unpack(c, d_raw, n, stride, dst.as<float4>()));
+  return LIOGPU_OK;
+}
+
+// packed float4 -> caller cloud (host or device)
+int store_cloud(Ctx* c, const float4* src, int n, void* dst, int stride) {
+  if (n <= 0) return LIOGPU_OK;
+  if (!dst || !stride_ok(stride)) { c->err = "bad output pointer / stride"; return LIOGPU_E_INVALID; }
+  const bool dev = is_device_ptr(dst);
+  if (stride == 16) {
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst, src, (size_t)n * 16, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  } else if (dev) {
+    LIOGPU_CUDA_OK(c, launch_pack(c, src, n, dst, stride));
+  } else {
+    LIOGPU_CUDA_OK(c, c->raw_out.reserve((size_t)n * stride));
+    LIOGPU_CUDA_OK(c, launch_pack(c, src, n, c->raw_out.p, stride));
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst, c->raw_out.p, (size_t)n * stride, cudaMemcpyDeviceToHost, c->stream));
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return LIOGPU_OK;
+}
+
+int enter(liogpu_ctx* ctx) {
+  if (!ctx) return LIOGPU_E_INVALID;
+  ctx->c.err.clear();
+  if (cudaSetDevice(ctx->c.device) != cudaSuccess) {
+    ctx->c.err = std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError());
+    return LIOGPU_E_CUDA;
+  }
+  return LIOGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int liogpu_abi_version(void) { return LIOGPU_ABI_VERSION; }
+
+void liogpu_default_params(liogpu_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->device = 0;
+  p->n_scan = 16;                                   // utility.h:275
+  p->horizon_scan = 1800;                           // :276
+  p->mapping_surf_leaf_size = 0.2f;                 // :303
+  p->surrounding_keyframe_map_leaf_size = 0.2f;     // :304
+  p->downsample_rate = 1;                           // :277
+  p->point_filter_num = 3;                          // :278
+  p->lidar_min_front = 1.0f;                        // :280
+  p->lidar_min_back = 5.0f;                         // :281
+  p->lidar_min_left = 2.0f;                         // :282
+  p->lidar_min_right = 2.0f;                        // :283
+  p->lidar_max_range = 1000.0f;                     // :284
+  p->lidar_max_intensity = 100.0f;                  // :285
+  p->knn_cell_size = 0.0f;
+}
+
+int liogpu_create(liogpu_ctx** out, const liogpu_params* params) {
+  if (!out || !params) return LIOGPU_E_INVALID;
+  *out = nullptr;
+  if (params->downsample_rate < 1 || params->point_filter_num < 1 || params->n_scan < 1) return LIOGPU_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || params->device < 0 || params->device >= ndev) {
+    cudaGetLastError();
+    return LIOGPU_E_CUDA;  // no CPU fallback by design
+  }
+  if (cudaSetDevice(params->device) != cudaSuccess) return LIOGPU_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, params->device) != cudaSuccess) return LIOGPU_E_CUDA;
+  if (prop.major < 10) return LIOGPU_E_CUDA;  // built for sm_100a only
+  liogpu_ctx* ctx = new (std::nothrow) liogpu_ctx();
+  if (!ctx) return LIOGPU_E_INVALID;
+  Ctx& c = ctx->c;
+  c.prm = *params;
+  c.device = params->device;
+  c.sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess ||
+      cudaHostAlloc(&c.h_pinned, 131072, cudaHostAllocDefault) != cudaSuccess) {
+    liogpu_destroy(ctx);
+    return LIOGPU_E_CUDA;
+  }
+  // scratch hint of allocateMemory (mapOptmization.cpp:333-335)
+  const size_t hint = (size_t)params->n_scan * (size_t)(params->horizon_scan > 0 ? params->horizon_scan : 1);
+  c.scan4.reserve(hint * sizeof(float4));
+  c.scan_ds4.reserve(hint * sizeof(float4));
+  *out = ctx;
+  return LIOGPU_OK;
+}
+
+void liogpu_destroy(liogpu_ctx* ctx) {
+  if (!ctx) return;
+  Ctx& c = ctx->c;
+  cudaSetDevice(c.device);
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
+                    &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
+                    &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
+                    &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& kv : c.keyframes) kv.second.first.release();
+  if (c.h_pinned) cudaFreeHost(c.h_pinned);
+  if (c.ev0) cudaEventDestroy(c.ev0);
+  if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete ctx;
+}
+
+const char* liogpu_last_error(const liogpu_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
+
+void* liogpu_host_alloc(unsigned long long bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void liogpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double time_scan_cur, const double* imu_time,
+                  const double* imu_rot_x, const double* imu_rot_y, const double* imu_rot_z, int n_imu,
+                  int deskew_enabled, void* xyzi_out, int out_stride, int cap_out, int* n_out) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!n_out || n < 0 || (n > 0 && !xyzirt) || stride < 28 || (stride % 4) != 0 || n_imu < 0 || n_imu > 2000 ||
+      (n_imu > 0 && (!imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z))) {
+    c->err = "liogpu_deskew: bad arguments";
+    return LIOGPU_E_INVALID;
+  }
+  *n_out = 0;
+  if (n == 0) return LIOGPU_OK;
+  const void* d_raw = xyzirt;
+  if (!is_device_ptr(xyzirt)) {
+    LIOGPU_CUDA_OK(c, c->raw_in.reserve((size_t)n * stride));
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(c->raw_in.p, xyzirt, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    d_raw = c->raw_in.p;
+  }
+  double* tab = reinterpret_cast<double*>((char*)c->h_pinned + 65536);  // 4 x 2000 doubles = 64000 B
+  for (int k = 0; k < n_imu; ++k) {
+    tab[k] = imu_time[k];
+    tab[n_imu + k] = imu_rot_x[k];
+    tab[2 * n_imu + k] = imu_rot_y[k];
+    tab[3 * n_imu + k] = imu_rot_z[k];
+  }
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  int m = 0;
+  rc = deskew_dev(c, d_raw, n, stride, time_scan_cur, tab, n_imu, deskew_enabled, c->dsk_scan, &m);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_out = m;
+  if (xyzi_out) {
+    if (m > cap_out) { c->err = "liogpu_deskew: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, c->dsk_scan.as<float4>(), m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return LIOGPU_OK;
+}
+
+int liogpu_transform_cloud(liogpu_ctx* ctx, const void* xyzi, int n, int stride, const float pose6[6], void* xyzi_out,
+                           int out_stride) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!pose6) { c->err = "null pose"; return LIOGPU_E_INVALID; }
+  rc = load_cloud(c, xyzi, n, stride, c->scan4);
+  if (rc) return rc;
+  if (n == 0) return LIOGPU_OK;
+  LIOGPU_CUDA_OK(c, c->misc.reserve(256));
+  LIOGPU_CUDA_OK(c, c->scan_ds4.reserve((size_t)n * sizeof(float4)));
+  float* hp = reinterpret_cast<float*>((char*)c->h_pinned + 3200);
+  for (int k = 0; k < 6; ++k) hp[k] = pose6[k];
+  float* d_pose = c->misc.as<float>() + 32;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d_pose, hp, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  LIOGPU_CUDA_OK(c, launch_transform(c, c->scan4.as<float4>(), n, d_pose, c->scan_ds4.as<float4>()));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  rc = store_cloud(c, c->scan_ds4.as<float4>(), n, xyzi_out, out_stride);
+  if (rc) return rc;
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return LIOGPU_OK;
+}
+
+int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride, float leaf, void* xyzi_out,
+                            int out_stride, int cap_out, int* n_out) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!n_out) { c->err = "null n_out"; return LIOGPU_E_INVALID; }
+  *n_out = 0;
+  rc = load_cloud(c, xyzi, n, stride, c->scan4);
+  if (rc) return rc;
+  if (n == 0) return LIOGPU_OK;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  int m = 0;
+  bool overflow = false;
+  rc = voxel_downsample_dev(c, c->scan4.as<float4>(), n, leaf, c->scan_ds4, &m, &overflow);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_out = m;
+  if (xyzi_out) {
+    if (m > cap_out) { c->err = "liogpu_voxel_downsample: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, c->scan_ds4.as<float4>(), m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int stride) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  auto& slot = c->keyframes[id];
+  rc = load_cloud(c, xyzi, n, stride, slot.first);
+  if (rc) { c->keyframes.erase(id); return rc; }
+  slot.second = n;
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));  // raw_in staging is reused by the next call
+  return LIOGPU_OK;
+}
+
+int liogpu_keyframe_clear(liogpu_ctx* ctx) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->keyframes) kv.second.first.release();
+  c->keyframes.clear();
+  return LIOGPU_OK;
+}
+
+int liogpu_keyframe_count(const liogpu_ctx* ctx) { return ctx ? (int)ctx->c.keyframes.size() : 0; }
+
+int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, int* n_map,
+                           void* xyzi_out, int out_stride, int cap_out) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (k < 0 || (k > 0 && (!ids || !pose6s)) || !n_map) { c->err = "liogpu_build_local_map: bad arguments"; return LIOGPU_E_INVALID; }
+  *n_map = 0;
+  size_t total = 0;
+  for (int f = 0; f < k; ++f) {
+    auto it = c->keyframes.find(ids[f]);
+    if (it == c->keyframes.end()) { c->err = "liogpu_build_local_map: unknown keyframe id"; return LIOGPU_E_NO_KEYFRAME; }
+    total += (size_t)it->second.second;
+  }
+  if (total > 0x7fffffffULL) { c->err = "local map too large"; return LIOGPU_E_INVALID; }
+  c->grid_valid = false;
+  c->n_map = 0;
+  if (total == 0) return LIOGPU_W_NO_KEYFRAMES;
+  LIOGPU_CUDA_OK(c, c->map_raw4.reserve(total * sizeof(float4)));
+  LIOGPU_CUDA_OK(c, c->misc.reserve(256));
+  if ((size_t)k * 6 * sizeof(float) > 32768) {
+    c->err = "too many keyframes in one local map (max 1365)";
+    return LIOGPU_E_INVALID;
+  }
+  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve((size_t)k * 6 * sizeof(float) + 64));  // pose table (scratch)
+  float* hposes = reinterpret_cast<float*>((char*)c->h_pinned + 8192);
+  std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
+  float* d_poses = c->dbg_d2.as<float>();
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d_poses, hposes, (size_t)k * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  size_t off = 0;
+  for (int f = 0; f < k; ++f) {  // transformPointCloud + "+=" concatenation (mapOptmization.cpp:1566-1576)
+    auto& kf = c->keyframes[ids[f]];
+    LIOGPU_CUDA_OK(c, launch_transform(c, kf.first.as<float4>(), kf.second, d_poses + 6 * f,
+                                       c->map_raw4.as<float4>() + off));
+    off += (size_t)kf.second;
+  }
+  int m = 0;
+  bool overflow = false;
+  rc = voxel_downsample_dev(c, c->map_raw4.as<float4>(), (int)total, leaf, c->map4, &m, &overflow);
+  if (rc) return rc;
+  rc = grid_build_dev(c, c->map4.as<float4>(), m);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_map = m;
+  if (xyzi_out) {
+    if (m > cap_out) { c->err = "liogpu_build_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, c->map4.as<float4>(), m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  c->grid_valid = false;
+  rc = load_cloud(c, xyzi, n, stride, c->map4);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  rc = grid_build_dev(c, c->map4.as<float4>(), n);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  if (n == 0) { c->grid_valid = true; c->n_map = 0; }
+  return LIOGPU_OK;
+}
+
+int liogpu_local_map_size(const liogpu_ctx* ctx) { return ctx ? ctx->c.n_map : 0; }
+
+static int s2m_guards(Ctx* c, int n, liogpu_s2m_info* info) {
+  if (info) {
+    std::memset(info, 0, sizeof(*info));
+    info->n_query = n;
+  }
+  if (!c->grid_valid) { c->err = "no local map installed"; return LIOGPU_E_NO_MAP; }
+  if (c->n_map <= 0) return LIOGPU_W_NO_KEYFRAMES;  // mapOptmization.cpp:1841
+  if (!(n > 30)) return LIOGPU_W_FEW_FEATURES;      // :1844
+  return LIOGPU_OK;
+}
+
+int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6], float matP_io[36],
+                    int* degenerate_io, int max_iter, liogpu_s2m_info* info) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!pose_io || !matP_io || !degenerate_io) { c->err = "liogpu_scan2map: null state pointer"; return LIOGPU_E_INVALID; }
+  rc = s2m_guards(c, n, info);
+  if (rc) {
+    if (info) info->is_degenerate = *degenerate_io;
+    return rc;
+  }
+  rc = load_cloud(c, scan_ds, n, stride, c->scan_ds4);
+  if (rc) return rc;
+  return scan2map_dev(c, c->scan_ds4.as<float4>(), n, pose_io, matP_io, degenerate_io, max_iter, info);
+}
+
+int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int stride, float pose_io[6],
+                               float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info, int* n_ds,
+                               void* scan_ds_out, int out_stride, int cap_out) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!pose_io || !matP_io || !degenerate_io || !n_ds) { c->err = "liogpu_downsample_scan2map: null pointer"; return LIOGPU_E_INVALID; }
+  *n_ds = 0;
+  rc = load_cloud(c, scan, n, stride, c->scan4);
+  if (rc) return rc;
+  int m = 0;
+  bool overflow = false;
+  rc = voxel_downsample_dev(c, c->scan4.as<float4>(), n, c->prm.mapping_surf_leaf_size, c->scan_ds4, &m, &overflow);
+  if (rc) return rc;
+  *n_ds = m;
+  if (scan_ds_out) {
+    if (m > cap_out) { c->err = "liogpu_downsample_scan2map: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, c->scan_ds4.as<float4>(), m, scan_ds_out, out_stride);
+    if (rc) return rc;
+  }
+  rc = s2m_guards(c, m, info);
+  if (rc) {
+    if (info) info->is_degenerate = *degenerate_io;
+    return rc;
+  }
+  rc = scan2map_dev(c, c->scan_ds4.as<float4>(), m, pose_io, matP_io, degenerate_io, max_iter, info);
+  if (rc) return rc;
+  return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, const float* pose6,
+                             const float* T12, int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag,
+                             unsigned char* tie) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!c->grid_valid) { c->err = "no local map installed"; return LIOGPU_E_NO_MAP; }
+  if (c->n_map <= 0 || c->grid.n_points <= 0) {  // empty map: no neighbours, nothing accepted
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j < 5; ++j) {
+        if (nn_idx) nn_idx[i * 5 + j] = -1;
+        if (nn_d2) nn_d2[i * 5 + j] = 1.0f;
+      }
+      if (coeff) coeff[i * 4] = coeff[i * 4 + 1] = coeff[i * 4 + 2] = coeff[i * 4 + 3] = 0.f;
+      if (flag) flag[i] = 0;
+      if (tie) tie[i] = 0;
+    }
+    return LIOGPU_OK;
+  }
+  rc = load_cloud(c, scan_ds, n, stride, c->scan_ds4);
+  if (rc) return rc;
+  return surf_optimization_dev(c, c->scan_ds4.as<float4>(), n, pose6, T12, nn_idx, nn_d2, coeff, flag, tie);
+}
+
+float liogpu_last_gpu_ms(const liogpu_ctx* ctx) { return ctx ? ctx->c.last_ms : 0.f; }
+unsigned long long liogpu_launch_count(const liogpu_ctx* ctx) { return ctx ? ctx->c.launches : 0ULL; }
+void* liogpu_stream(const liogpu_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+}  // extern "C"

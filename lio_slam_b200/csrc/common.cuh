@@ -1,0 +1,147 @@
+// common.cuh — shared definitions of libliogpu (sm_100a).  Product code: never includes oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/liogpu.h"
+
+namespace liogpu {
+
+// ---- device buffer that grows on demand (steady state: no allocation on the per-scan path) ----
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = bytes + bytes / 4 + 256;
+    void* np_ = nullptr;
+    cudaError_t e = cudaMalloc(&np_, want);
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = np_;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- voxel grid parameters computed on device by voxel_setup_kernel ----
+struct VoxelSetup {
+  float min_p[3], max_p[3];
+  float inv_leaf;
+  int min_b[3];
+  int div_b[3];
+  int mul1, mul2;
+  int overflow;       // 1 = guard fired (output = input)
+  unsigned n_cells;   // div.x*div.y*div.z (valid when !overflow)
+  int n_valid;        // finite points
+  int key_bits;       // bits needed to sort keys in [0, n_cells]
+};
+
+// ---- sorted-grid 5-NN index over the local map ----
+struct GridParams {
+  float ox, oy, oz;   // origin = per-axis minimum of the map
+  float h, inv_h;     // cell edge
+  float slack;        // positional slack covering f32 rounding of the cell assignment
+  int nx, ny, nz;
+  int n_points;
+  unsigned n_cells;
+  float gate_d2;      // squared search radius (1.0 for surfOptimization, MO:1641)
+};
+
+// ---- state of the LM loop kept on device between iterations (MO:171,176,177) ----
+struct LmDevState {
+  float pose[6];
+  float matP[36];
+  int degenerate;
+  int iter;        // iterations executed so far
+  int done;        // converged or max_iter reached
+  int converged;
+  int max_iter;
+  int n_sel;
+  int tie_queries;
+  float delta_r, delta_t;
+  double JtJ[36];
+  double Jtr[6];
+  float pose_hist[LIOGPU_MAX_ITER][6];
+  int nsel_hist[LIOGPU_MAX_ITER];
+};
+
+// host-visible context
+struct Ctx {
+  liogpu_params prm;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  unsigned long long launches = 0;
+  float last_ms = 0.f;
+
+  // staging
+  DevBuf raw_in, raw_out;
+  // scan / queries
+  DevBuf scan4, scan_ds4;
+  // local map + grid
+  DevBuf map_raw4, map4, map_sorted, cell_start;
+  int n_map = 0;
+  bool grid_valid = false;
+  GridParams grid{};
+  // sort + scan scratch
+  DevBuf keys0, keys1, vals0, vals1, counters, scan_tmp, seg_flag, seg_start;
+  // small device structs
+  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc;
+  // per-point debug outputs of surf_optimization
+  DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
+  // pinned host mirrors
+  void* h_pinned = nullptr;  // 128 KiB: small readbacks in the first 64 KiB, IMU table in the second
+  // keyframes (lidar frame, packed float4)
+  std::map<int, std::pair<DevBuf, int>> keyframes;
+  // deskew
+  DevBuf imu_tab, dsk_flags, dsk_scan;
+};
+
+#define LIOGPU_CUDA_OK(ctx, expr)                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                  \
+      return LIOGPU_E_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+// kernels' launch wrappers (each returns cudaError_t from cudaGetLastError)
+// --- layout.cu
+cudaError_t launch_unpack(Ctx* c, const void* d_raw, int n, int stride, float4* out);
+cudaError_t launch_pack(Ctx* c, const float4* in, int n, void* d_raw, int stride);
+cudaError_t launch_transform(Ctx* c, const float4* in, int n, const float* d_pose6, float4* out);
+// --- sort.cu
+cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, uint32_t** keys_out, uint32_t** vals_out);
+cudaError_t exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, int n, uint32_t* d_total);
+// --- voxel.cu
+cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm);
+int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& out, int* n_out, bool* overflow);
+// --- grid.cu
+int grid_build_dev(Ctx* c, const float4* map4, int n);
+// --- s2m.cu
+int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                 int max_iter, liogpu_s2m_info* info);
+int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6, const float* T12, int* nn_idx,
+                          float* nn_d2, float* coeff, unsigned char* flag, unsigned char* tie);
+// --- deskew.cu
+int deskew_dev(Ctx* c, const void* d_raw, int n, int stride, double t_scan, const double* imu4_host, int n_imu,
+               int enabled, DevBuf& out, int* n_out);
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace liogpu

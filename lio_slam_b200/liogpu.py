@@ -1,0 +1,281 @@
+"""ctypes binding of libliogpu.so — the C ABI declared in include/liogpu.h.
+
+This is plumbing for tests and bench.py; the product is the shared library.  There is no CPU path:
+if the library is missing or no sm_100 GPU is usable, construction raises.
+
+Clouds may be passed as
+  * (n,4) float32 arrays  (packed x,y,z,intensity; stride 16), or
+  * structured arrays with itemsize 32 (pcl::PointXYZI / PointXYZIRT records; stride 32), or
+  * (device_ptr:int, n, stride) tuples for buffers already resident on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libliogpu.so")
+
+LIOGPU_MAX_ITER = 30
+OK = 0
+E_INVALID, E_CUDA, E_NO_MAP, E_NO_KEYFRAME, E_CAPACITY = -1, -2, -3, -4, -5
+W_LEAF_OVERFLOW, W_FEW_FEATURES, W_NO_KEYFRAMES = 1, 2, 3
+
+
+class Params(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_scan", C.c_int), ("horizon_scan", C.c_int),
+                ("mapping_surf_leaf_size", C.c_float), ("surrounding_keyframe_map_leaf_size", C.c_float),
+                ("downsample_rate", C.c_int), ("point_filter_num", C.c_int),
+                ("lidar_min_front", C.c_float), ("lidar_min_back", C.c_float), ("lidar_min_left", C.c_float),
+                ("lidar_min_right", C.c_float), ("lidar_max_range", C.c_float), ("lidar_max_intensity", C.c_float),
+                ("knn_cell_size", C.c_float), ("reserved", C.c_int * 7)]
+
+
+class S2MInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("n_query", C.c_int), ("n_sel", C.c_int),
+                ("is_degenerate", C.c_int), ("tie_queries", C.c_int), ("delta_r_deg", C.c_float),
+                ("delta_t_cm", C.c_float), ("JtJ", C.c_double * 36), ("Jtr", C.c_double * 6),
+                ("pose_hist", (C.c_float * 6) * LIOGPU_MAX_ITER), ("nsel_hist", C.c_int * LIOGPU_MAX_ITER),
+                ("gpu_ms", C.c_float)]
+
+
+EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liogpu_destroy", "liogpu_last_error",
+           "liogpu_host_alloc", "liogpu_host_free", "liogpu_deskew", "liogpu_transform_cloud",
+           "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
+           "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
+           "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
+           "liogpu_stream"]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libliogpu.so (built in-tree by __graft_entry__.build()).  Fails loudly when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.liogpu_last_error.restype = C.c_char_p
+    lib.liogpu_last_error.argtypes = [C.c_void_p]
+    lib.liogpu_host_alloc.restype = C.c_void_p
+    lib.liogpu_host_alloc.argtypes = [C.c_ulonglong]
+    lib.liogpu_host_free.argtypes = [C.c_void_p]
+    lib.liogpu_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params)]
+    lib.liogpu_destroy.argtypes = [C.c_void_p]
+    lib.liogpu_last_gpu_ms.restype = C.c_float
+    lib.liogpu_last_gpu_ms.argtypes = [C.c_void_p]
+    lib.liogpu_launch_count.restype = C.c_ulonglong
+    lib.liogpu_launch_count.argtypes = [C.c_void_p]
+    lib.liogpu_stream.restype = C.c_void_p
+    lib.liogpu_stream.argtypes = [C.c_void_p]
+    lib.liogpu_keyframe_count.argtypes = [C.c_void_p]
+    lib.liogpu_local_map_size.argtypes = [C.c_void_p]
+    lib.liogpu_keyframe_clear.argtypes = [C.c_void_p]
+    lib.liogpu_deskew.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                  C.POINTER(C.c_int)]
+    lib.liogpu_transform_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.liogpu_voxel_downsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                            C.c_int, C.POINTER(C.c_int)]
+    lib.liogpu_keyframe_put.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_build_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                           C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo)]
+    lib.liogpu_downsample_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo), C.POINTER(C.c_int),
+                                               C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_surf_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def default_params(**over) -> Params:
+    p = Params()
+    load_library().liogpu_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+class LioGpuError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"liogpu status {status}: {msg}")
+        self.status = status
+
+
+def _cloud_args(cloud):
+    """-> (pointer:int, n, stride, keepalive)"""
+    if isinstance(cloud, tuple):
+        ptr, n, stride = cloud
+        return int(ptr), int(n), int(stride), None
+    a = cloud
+    if a.dtype.fields is not None:
+        a = np.ascontiguousarray(a)
+        return a.ctypes.data, a.shape[0], a.dtype.itemsize, a
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] in (4, 8), "packed clouds are (n,4) float32 (or (n,8) for 32-byte records)"
+    return a.ctypes.data, a.shape[0], a.shape[1] * 4, a
+
+
+def info_to_dict(info: S2MInfo) -> dict:
+    it = info.iterations
+    return dict(iterations=it, converged=bool(info.converged), n_query=info.n_query, n_sel=info.n_sel,
+                is_degenerate=info.is_degenerate, tie_queries=info.tie_queries, delta_r=info.delta_r_deg,
+                delta_t=info.delta_t_cm, JtJ=np.array(info.JtJ).reshape(6, 6), Jtr=np.array(info.Jtr),
+                pose_hist=np.array(info.pose_hist, dtype=np.float32).reshape(LIOGPU_MAX_ITER, 6)[:it],
+                nsel_hist=np.array(info.nsel_hist)[:it], gpu_ms=info.gpu_ms)
+
+
+class LioGpu:
+    """One liogpu context (one GPU, one stream)."""
+
+    def __init__(self, params: Params | None = None, **over):
+        self.lib = load_library()
+        self.params = params if params is not None else default_params(**over)
+        h = C.c_void_p()
+        st = self.lib.liogpu_create(C.byref(h), C.byref(self.params))
+        if st != OK:
+            raise LioGpuError(st, "liogpu_create failed (no usable sm_100 CUDA device? there is no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.liogpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int) -> int:
+        if st < 0:
+            raise LioGpuError(st, self.lib.liogpu_last_error(self.h).decode())
+        return st
+
+    # --------------------------------------------------------------------------------------------
+    def last_gpu_ms(self) -> float:
+        return float(self.lib.liogpu_last_gpu_ms(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.liogpu_launch_count(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.liogpu_stream(self.h) or 0)
+
+    def deskew(self, scan_xyzirt, time_scan_cur: float, imu_t, rx, ry, rz, deskew_enabled: bool = True):
+        ptr, n, stride, keep = _cloud_args(scan_xyzirt)
+        imu_t = np.ascontiguousarray(imu_t, np.float64); rx = np.ascontiguousarray(rx, np.float64)
+        ry = np.ascontiguousarray(ry, np.float64); rz = np.ascontiguousarray(rz, np.float64)
+        out = np.empty((max(n, 1), 4), np.float32)
+        n_out = C.c_int(0)
+        st = self._check(self.lib.liogpu_deskew(self.h, ptr, n, stride, C.c_double(time_scan_cur), imu_t.ctypes.data,
+                                                rx.ctypes.data, ry.ctypes.data, rz.ctypes.data, imu_t.shape[0],
+                                                int(deskew_enabled), out.ctypes.data, 16, out.shape[0],
+                                                C.byref(n_out)))
+        return out[: n_out.value].copy(), st
+
+    def transform_cloud(self, cloud, pose6) -> np.ndarray:
+        ptr, n, stride, keep = _cloud_args(cloud)
+        pose = np.ascontiguousarray(pose6, np.float32)
+        out = np.empty((n, 4), np.float32)
+        self._check(self.lib.liogpu_transform_cloud(self.h, ptr, n, stride, pose.ctypes.data, out.ctypes.data, 16))
+        return out
+
+    def voxel_downsample(self, cloud, leaf: float, out_stride: int = 16):
+        ptr, n, stride, keep = _cloud_args(cloud)
+        out = np.empty((max(n, 1), out_stride // 4), np.float32)
+        n_out = C.c_int(0)
+        st = self._check(self.lib.liogpu_voxel_downsample(self.h, ptr, n, stride, C.c_float(leaf), out.ctypes.data,
+                                                          out_stride, out.shape[0], C.byref(n_out)))
+        return out[: n_out.value].copy(), st
+
+    def keyframe_put(self, kid: int, cloud) -> None:
+        ptr, n, stride, keep = _cloud_args(cloud)
+        self._check(self.lib.liogpu_keyframe_put(self.h, int(kid), ptr, n, stride))
+
+    def keyframe_clear(self) -> None:
+        self._check(self.lib.liogpu_keyframe_clear(self.h))
+
+    def keyframe_count(self) -> int:
+        return int(self.lib.liogpu_keyframe_count(self.h))
+
+    def build_local_map(self, ids, poses, leaf: float, fetch: bool = True, cap: int | None = None):
+        ids = np.ascontiguousarray(ids, np.int32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        assert poses.shape[0] == ids.shape[0]
+        n_map = C.c_int(0)
+        if fetch:
+            out = np.empty((int(cap or 1), 4), np.float32)
+            st = self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                                 C.c_float(leaf), C.byref(n_map), out.ctypes.data, 16, out.shape[0])
+            if st == E_CAPACITY:  # retry with the reported size
+                out = np.empty((n_map.value, 4), np.float32)
+                st = self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                                     C.c_float(leaf), C.byref(n_map), out.ctypes.data, 16,
+                                                     out.shape[0])
+            self._check(st)
+            return out[: n_map.value].copy(), st
+        st = self._check(self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                                         C.c_float(leaf), C.byref(n_map), None, 16, 0))
+        return n_map.value, st
+
+    def set_local_map(self, cloud) -> None:
+        ptr, n, stride, keep = _cloud_args(cloud)
+        self._check(self.lib.liogpu_set_local_map(self.h, ptr, n, stride))
+
+    def local_map_size(self) -> int:
+        return int(self.lib.liogpu_local_map_size(self.h))
+
+    def scan2map(self, scan_ds, pose6, matP=None, degenerate: int = 0, max_iter: int = 30, raw_info: bool = False):
+        ptr, n, stride, keep = _cloud_args(scan_ds)
+        pose = np.array(pose6, dtype=np.float32)
+        P = np.zeros(36, np.float32) if matP is None else np.array(matP, dtype=np.float32).reshape(36)
+        deg = C.c_int(int(degenerate))
+        info = S2MInfo()
+        st = self._check(self.lib.liogpu_scan2map(self.h, ptr, n, stride, pose.ctypes.data, P.ctypes.data,
+                                                  C.byref(deg), max_iter, C.byref(info)))
+        d = info if raw_info else info_to_dict(info)
+        if not raw_info:
+            d["status"] = st
+            d["is_degenerate"] = deg.value
+        return pose, P.reshape(6, 6), d
+
+    def downsample_scan2map(self, scan, pose6, matP=None, degenerate: int = 0, max_iter: int = 30, fetch_ds=False):
+        ptr, n, stride, keep = _cloud_args(scan)
+        pose = np.array(pose6, dtype=np.float32)
+        P = np.zeros(36, np.float32) if matP is None else np.array(matP, dtype=np.float32).reshape(36)
+        deg = C.c_int(int(degenerate))
+        info = S2MInfo()
+        n_ds = C.c_int(0)
+        out = np.empty((max(n, 1), 4), np.float32) if fetch_ds else None
+        st = self._check(self.lib.liogpu_downsample_scan2map(
+            self.h, ptr, n, stride, pose.ctypes.data, P.ctypes.data, C.byref(deg), max_iter, C.byref(info),
+            C.byref(n_ds), out.ctypes.data if fetch_ds else None, 16, out.shape[0] if fetch_ds else 0))
+        d = info_to_dict(info)
+        d["status"] = st
+        d["is_degenerate"] = deg.value
+        d["n_ds"] = n_ds.value
+        if fetch_ds:
+            d["scan_ds"] = out[: n_ds.value].copy()
+        return pose, P.reshape(6, 6), d
+
+    def surf_optimization(self, scan_ds, pose6=None, T12=None):
+        ptr, n, stride, keep = _cloud_args(scan_ds)
+        idx = np.empty((n, 5), np.int32); d2 = np.empty((n, 5), np.float32)
+        coeff = np.empty((n, 4), np.float32); flag = np.empty(n, np.uint8); tie = np.empty(n, np.uint8)
+        pose = np.ascontiguousarray(pose6, np.float32) if pose6 is not None else None
+        T = np.ascontiguousarray(T12, np.float32) if T12 is not None else None
+        self._check(self.lib.liogpu_surf_optimization(
+            self.h, ptr, n, stride, pose.ctypes.data if pose is not None else None,
+            T.ctypes.data if T is not None else None, idx.ctypes.data, d2.ctypes.data, coeff.ctypes.data,
+            flag.ctypes.data, tie.ctypes.data))
+        return dict(nn_idx=idx, nn_d2=d2, coeff=coeff, flag=flag, tie=tie)

@@ -1,0 +1,633 @@
+// liorf_oracle_core.h — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// A dependency-free C++14 restatement of liorf's scan-to-map registration hot path, used ONLY by
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the checker
+// for the CUDA library.  Nothing under lio_slam_b200/ includes, links or calls this.
+//
+// PARITY UNPINNED: the reference (/root/reference, JiLiBIT/LIO-SLAM) ships no tests, golden vectors
+// or fixtures for this path and cannot be built here (needs ROS, PCL, FLANN, Eigen, OpenCV, GTSAM —
+// none installed, none vendored, all version-unpinned in src/liorf/CMakeLists.txt:27-34).  Each
+// function below cites the reference lines it follows (MO = src/liorf/src/mapOptmization.cpp,
+// IP = src/liorf/src/imageProjection.cpp) and, where the arithmetic lives in a third-party library,
+// restates that library's published algorithm (PCL 1.10 VoxelGrid / getTransformation, FLANN 1.9.1
+// L2_Simple exact k-NN, Eigen 3.3.7 ColPivHouseholderQR, OpenCV 4.x gemm/QR solve/Jacobi eigen/LU
+// inverse).  The OpenCV pieces ARE pinned against the real library: tests/test_oracle_cv2.py checks
+// them against Python cv2 4.13 (available in this image) and against fixtures it generated.
+//
+// Build: g++ -O2 -std=c++14 -ffp-contract=off -fopenmp (x86-64 baseline: no FMA, like a stock
+// Ubuntu build of the reference).  Every float expression is written in the operation order of the
+// cited source so that "bit-exact" is well defined.
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace liorf_oracle {
+
+struct P4 {  // packed point: x, y, z, intensity  (pcl::PointXYZI without its padding, UT:65)
+  float x, y, z, i;
+};
+
+// ---------------------------------------------------------------------------------------------
+// a6: pcl::getTransformation(x,y,z,roll,pitch,yaw) as used by trans2Affine3f (MO:887-890) and
+// transformPointCloud (MO:856).  Rz*Ry*Rx, f32 products.  Canonical trig: f64 sin/cos rounded to
+// f32 (glibc sinf/cosf are <1 ulp but not reproducible on a GPU; SURVEY §7 "transform drift").
+// T is row-major 3x4.
+inline void pose_to_T(const float pose[6], float T[12]) {
+  const float roll = pose[0], pitch = pose[1], yaw = pose[2];
+  const float A = (float)std::cos((double)yaw), B = (float)std::sin((double)yaw);
+  const float C = (float)std::cos((double)pitch), D = (float)std::sin((double)pitch);
+  const float E = (float)std::cos((double)roll), F = (float)std::sin((double)roll);
+  const float DE = D * E, DF = D * F;
+  T[0] = A * C;  T[1] = A * DF - B * E;  T[2] = B * F + A * DE;  T[3] = pose[3];
+  T[4] = B * C;  T[5] = A * E + B * DF;  T[6] = B * DE - A * F;  T[7] = pose[4];
+  T[8] = -D;     T[9] = C * F;           T[10] = C * E;          T[11] = pose[5];
+}
+
+// pointAssociateToMap (MO:841-847) / transformPointCloud body (MO:862-864): r0*x + r1*y + r2*z + t.
+inline P4 apply_T(const float T[12], const P4& p) {
+  P4 o;
+  o.x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
+  o.y = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
+  o.z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
+  o.i = p.i;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a3/a4: pcl::VoxelGrid<PointXYZI>::applyFilter (call sites MO:1536,1582,1609); SURVEY A.1.
+// Canonical within-voxel order = ascending input index (stable sort).  Returns 1 when the overflow
+// guard fired (output = input), else 0.
+inline int voxel_grid(const P4* in, int n, float leaf, std::vector<P4>& out) {
+  out.clear();
+  if (n <= 0) return 0;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = 0; i < n; ++i) {
+    const P4& p = in[i];
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
+    mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
+  }
+  const float inv = 1.0f / leaf;
+  int64_t d[3];
+  for (int a = 0; a < 3; ++a) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+  if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX) {  // overflow guard (q4)
+    out.assign(in, in + n);
+    return 1;
+  }
+  int minb[3], maxb[3], div[3];
+  for (int a = 0; a < 3; ++a) {
+    minb[a] = (int)std::floor(mn[a] * inv);
+    maxb[a] = (int)std::floor(mx[a] * inv);
+    div[a] = maxb[a] - minb[a] + 1;
+  }
+  const int mul1 = div[0], mul2 = div[0] * div[1];
+  std::vector<std::pair<uint32_t, int>> keys;
+  keys.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    const P4& p = in[i];
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    const int ix = (int)(std::floor(p.x * inv) - (float)minb[0]);
+    const int iy = (int)(std::floor(p.y * inv) - (float)minb[1]);
+    const int iz = (int)(std::floor(p.z * inv) - (float)minb[2]);
+    keys.emplace_back((uint32_t)(ix + iy * mul1 + iz * mul2), i);
+  }
+  std::stable_sort(keys.begin(), keys.end(),
+                   [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) {
+                     return a.first < b.first;
+                   });
+  size_t s = 0;
+  while (s < keys.size()) {
+    size_t e = s;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    while (e < keys.size() && keys[e].first == keys[s].first) {
+      const P4& p = in[keys[e].second];
+      sx += p.x; sy += p.y; sz += p.z; si += p.i;
+      ++e;
+    }
+    const float cnt = (float)(e - s);
+    out.push_back(P4{sx / cnt, sy / cnt, sz / cnt, si / cnt});
+    s = e;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7 (k-NN part): pcl::KdTreeFLANN::nearestKSearch(pointSel, 5, ...) (MO:1631); SURVEY A.2.
+// Distance = FLANN L2_Simple<float>: r = 0; r += d*d for x,y,z.  Canonical order: ascending
+// (d2, map index).  top[5] is the 6th-best, kept only to log equidistant ties.
+struct Knn6 {
+  float d2[6];
+  int idx[6];
+  inline void init() {
+    for (int k = 0; k < 6; ++k) { d2[k] = FLT_MAX; idx[k] = INT_MAX; }
+  }
+  inline bool better_than_worst(float d, int id) const {
+    return d < d2[5] || (d == d2[5] && id < idx[5]);
+  }
+  inline void insert(float d, int id) {
+    if (!better_than_worst(d, id)) return;
+    int k = 5;
+    while (k > 0 && (d < d2[k - 1] || (d == d2[k - 1] && id < idx[k - 1]))) {
+      d2[k] = d2[k - 1]; idx[k] = idx[k - 1];
+      --k;
+    }
+    d2[k] = d; idx[k] = id;
+  }
+  inline bool tie() const {
+    return d2[0] == d2[1] || d2[1] == d2[2] || d2[2] == d2[3] || d2[3] == d2[4] || d2[4] == d2[5];
+  }
+};
+
+inline float l2_simple(const P4& q, const P4& p) {
+  float r = 0.f;
+  float d = q.x - p.x; r += d * d;
+  d = q.y - p.y;       r += d * d;
+  d = q.z - p.z;       r += d * d;
+  return r;
+}
+
+inline void knn_brute(const P4* map, int nm, const P4& q, Knn6& r) {
+  r.init();
+  for (int j = 0; j < nm; ++j) r.insert(l2_simple(q, map[j]), j);
+}
+
+// An exact KD-tree of the FLANN KDTreeSingleIndex family (leaf_max_size 15, split on the widest
+// dimension at the median) so the timed CPU baseline has the reference's algorithmic shape (a5:
+// kdtreeSurfFromMap->setInputCloud, MO:1846).  Bounds are evaluated in f64 with a relative slack
+// so pruning can never drop a point whose f32 L2_Simple distance ties or beats the current worst.
+struct KdTree {
+  struct Node {
+    int left, right;  // children, or -1
+    int lo, hi;       // leaf: range in perm
+    int dim;
+    float cut_lo, cut_hi;
+  };
+  const P4* pts = nullptr;
+  int n = 0;
+  std::vector<int> perm;
+  std::vector<P4> reord;  // points in perm order (leaf scans are contiguous, like FLANN's reorder)
+  std::vector<Node> nodes;
+  float bb_lo[3], bb_hi[3];
+
+  static inline float coord(const P4& p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
+
+  void build(const P4* p, int count) {
+    pts = p; n = count;
+    perm.resize(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    nodes.clear();
+    nodes.reserve(n / 4 + 16);
+    for (int d = 0; d < 3; ++d) { bb_lo[d] = FLT_MAX; bb_hi[d] = -FLT_MAX; }
+    for (int i = 0; i < n; ++i)
+      for (int d = 0; d < 3; ++d) {
+        bb_lo[d] = std::min(bb_lo[d], coord(p[i], d));
+        bb_hi[d] = std::max(bb_hi[d], coord(p[i], d));
+      }
+    if (n > 0) build_rec(0, n);
+    reord.resize(n);
+    for (int i = 0; i < n; ++i) reord[i] = pts[perm[i]];
+  }
+  int build_rec(int lo, int hi) {
+    const int id = (int)nodes.size();
+    nodes.push_back(Node{-1, -1, lo, hi, 0, 0.f, 0.f});
+    if (hi - lo <= 15) return id;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = lo; i < hi; ++i)
+      for (int d = 0; d < 3; ++d) {
+        const float c = coord(pts[perm[i]], d);
+        mn[d] = std::min(mn[d], c); mx[d] = std::max(mx[d], c);
+      }
+    int dim = 0;
+    if (mx[1] - mn[1] > mx[dim] - mn[dim]) dim = 1;
+    if (mx[2] - mn[2] > mx[dim] - mn[dim]) dim = 2;
+    const int mid = (lo + hi) / 2;
+    std::nth_element(perm.begin() + lo, perm.begin() + mid, perm.begin() + hi,
+                     [&](int a, int b) { return coord(pts[a], dim) < coord(pts[b], dim); });
+    float lmax = -FLT_MAX, rmin = FLT_MAX;
+    for (int i = lo; i < mid; ++i) lmax = std::max(lmax, coord(pts[perm[i]], dim));
+    for (int i = mid; i < hi; ++i) rmin = std::min(rmin, coord(pts[perm[i]], dim));
+    const int l = build_rec(lo, mid);
+    const int r = build_rec(mid, hi);
+    nodes[id].left = l; nodes[id].right = r; nodes[id].dim = dim;
+    nodes[id].cut_lo = lmax; nodes[id].cut_hi = rmin;
+    return id;
+  }
+  void search_rec(int id, const P4& q, Knn6& r, double mind2, double off[3]) const {
+    const Node& nd = nodes[id];
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi; ++i) r.insert(l2_simple(q, reord[i]), perm[i]);
+      return;
+    }
+    const int d = nd.dim;
+    const double v = coord(q, d);
+    const double d1 = v - nd.cut_lo, d2 = v - nd.cut_hi;
+    int best, other;
+    double cut;
+    if (d1 + d2 < 0) { best = nd.left; other = nd.right; cut = d2 * d2; }
+    else { best = nd.right; other = nd.left; cut = d1 * d1; }
+    search_rec(best, q, r, mind2, off);
+    const double save = off[d];
+    const double m2 = mind2 + cut - save;
+    if (m2 * 0.999999 <= (double)r.d2[5]) {
+      off[d] = cut;
+      search_rec(other, q, r, m2, off);
+      off[d] = save;
+    }
+  }
+  void knn(const P4& q, Knn6& r) const {
+    r.init();
+    if (n == 0) return;
+    double off[3], mind2 = 0;
+    for (int d = 0; d < 3; ++d) {
+      const double v = coord(q, d);
+      double o = 0;
+      if (v < bb_lo[d]) o = (v - bb_lo[d]) * (v - bb_lo[d]);
+      if (v > bb_hi[d]) o = (v - bb_hi[d]) * (v - bb_hi[d]);
+      off[d] = o; mind2 += o;
+    }
+    search_rec(0, q, r, mind2, off);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// a7 (plane fit): Eigen::Matrix<float,5,3>::colPivHouseholderQr().solve(b) with b = -1 (MO:1633-1648).
+// Unblocked column-pivoted Householder QR as in Eigen 3.3.7 ColPivHouseholderQR::computeInPlace +
+// _solve_impl; reductions summed left to right; SURVEY A.3.  A is row-major 5x3 and is destroyed.
+inline void qr53_solve(float A[5][3], const float b[5], float x[3]) {
+  const int rows = 5, cols = 3;
+  float hc[3], normU[3], normD[3];
+  int perm[3] = {0, 1, 2};
+  for (int j = 0; j < cols; ++j) {
+    float s = 0.f;
+    for (int i = 0; i < rows; ++i) s += A[i][j] * A[i][j];
+    normD[j] = normU[j] = std::sqrt(s);
+  }
+  float maxn = normU[0];
+  if (normU[1] > maxn) maxn = normU[1];
+  if (normU[2] > maxn) maxn = normU[2];
+  const float th = (maxn * FLT_EPSILON) * (maxn * FLT_EPSILON) / (float)rows;
+  const float downdate_th = std::sqrt(FLT_EPSILON);
+  int nonzero = cols;
+  for (int k = 0; k < cols; ++k) {
+    int big = k;
+    for (int j = k + 1; j < cols; ++j)
+      if (normU[j] > normU[big]) big = j;
+    const float bigsq = normU[big] * normU[big];
+    if (nonzero == cols && bigsq < th * (float)(rows - k)) nonzero = k;
+    if (big != k) {
+      for (int i = 0; i < rows; ++i) std::swap(A[i][k], A[i][big]);
+      std::swap(normU[k], normU[big]);
+      std::swap(normD[k], normD[big]);
+      std::swap(perm[k], perm[big]);
+    }
+    // makeHouseholderInPlace on A[k..4][k]
+    float tail = 0.f;
+    for (int i = k + 1; i < rows; ++i) tail += A[i][k] * A[i][k];
+    const float c0 = A[k][k];
+    float beta, tau;
+    if (tail <= FLT_MIN) {
+      tau = 0.f; beta = c0;
+      for (int i = k + 1; i < rows; ++i) A[i][k] = 0.f;
+    } else {
+      beta = std::sqrt(c0 * c0 + tail);
+      if (c0 >= 0.f) beta = -beta;
+      const float den = c0 - beta;
+      for (int i = k + 1; i < rows; ++i) A[i][k] = A[i][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    A[k][k] = beta;
+    hc[k] = tau;
+    // applyHouseholderOnTheLeft to the trailing columns
+    if (tau != 0.f) {
+      for (int j = k + 1; j < cols; ++j) {
+        float tmp = 0.f;
+        for (int i = k + 1; i < rows; ++i) tmp += A[i][k] * A[i][j];
+        tmp += A[k][j];
+        A[k][j] -= tau * tmp;
+        for (int i = k + 1; i < rows; ++i) A[i][j] -= (tau * A[i][k]) * tmp;
+      }
+    }
+    // LAPACK-style norm down-dating
+    for (int j = k + 1; j < cols; ++j) {
+      if (normU[j] != 0.f) {
+        float temp = std::fabs(A[k][j]) / normU[j];
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        const float ratio = normU[j] / normD[j];
+        const float temp2 = temp * (ratio * ratio);
+        if (temp2 <= downdate_th) {
+          float s = 0.f;
+          for (int i = k + 1; i < rows; ++i) s += A[i][j] * A[i][j];
+          normD[j] = std::sqrt(s);
+          normU[j] = normD[j];
+        } else {
+          normU[j] *= std::sqrt(temp);
+        }
+      }
+    }
+  }
+  x[0] = x[1] = x[2] = 0.f;
+  if (nonzero == 0) return;
+  float c[5];
+  for (int i = 0; i < rows; ++i) c[i] = b[i];
+  for (int k = 0; k < nonzero; ++k) {  // c = H_k ... H_0 applied in order (Q^T b)
+    if (hc[k] == 0.f) continue;
+    float tmp = 0.f;
+    for (int i = k + 1; i < rows; ++i) tmp += A[i][k] * c[i];
+    tmp += c[k];
+    c[k] -= hc[k] * tmp;
+    for (int i = k + 1; i < rows; ++i) c[i] -= (hc[k] * A[i][k]) * tmp;
+  }
+  for (int i = nonzero - 1; i >= 0; --i) {  // column-oriented back substitution (col-major Eigen)
+    c[i] = c[i] / A[i][i];
+    for (int r = 0; r < i; ++r) c[r] -= c[i] * A[r][i];
+  }
+  for (int i = 0; i < nonzero; ++i) x[perm[i]] = c[i];
+}
+
+// a7 (per point): body of the OpenMP loop in surfOptimization (MO:1623-1686) after the k-NN.
+// nb = the 5 neighbours' coordinates in ascending (d2, idx) order, d2_4 = pointSearchSqDis[4].
+// Returns the flag; coeff = (s*pa, s*pb, s*pc, s*pd2).
+inline bool plane_residual(const P4& ori, const P4& sel, const P4 nb[5], float d2_4, P4& coeff) {
+  coeff = P4{0.f, 0.f, 0.f, 0.f};
+  if (!(d2_4 < 1.0)) return false;  // MO:1641
+  float A[5][3], b[5], x[3];
+  for (int j = 0; j < 5; ++j) {
+    A[j][0] = nb[j].x; A[j][1] = nb[j].y; A[j][2] = nb[j].z;
+    b[j] = -1.f;
+  }
+  qr53_solve(A, b, x);
+  float pa = x[0], pb = x[1], pc = x[2], pd = 1.f;
+  const float ps = std::sqrt(pa * pa + pb * pb + pc * pc);  // MO:1655
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  for (int j = 0; j < 5; ++j) {  // MO:1658-1666 (fabs(float) > 0.2 compares in double)
+    const float r = pa * nb[j].x + pb * nb[j].y + pc * nb[j].z + pd;
+    if ((double)std::fabs(r) > 0.2) return false;
+  }
+  const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;  // MO:1669
+  // MO:1671-1672: the 0.9 literal promotes the quotient to double; sqrt(sqrt(float)) stays float
+  const float r2 = ori.x * ori.x + ori.y * ori.y + ori.z * ori.z;
+  const float s = (float)(1.0 - 0.9 * (double)std::fabs(pd2) / (double)std::sqrt(std::sqrt(r2)));
+  if (!((double)s > 0.1)) return false;  // MO:1679 (coeffSelSurfVec[i] is only written when accepted)
+  coeff.x = s * pa; coeff.y = s * pb; coeff.z = s * pc; coeff.i = s * pd2;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OpenCV 4.x pieces of LMOptimization (MO:1781-1814); SURVEY A.4.  All row-major 6x6 f32.
+
+// cv::solve(A, b, x, DECOMP_QR) -> hal::QR32f -> QRImpl<float> (Householder, no pivoting), n=6, k=1.
+inline bool cv_solve6_qr(const float Ain[36], const float bin[6], float x[6]) {
+  const int m = 6, n = 6;
+  const float eps = FLT_EPSILON * 10;
+  float A[36], b[6], vl[6], hf[6];
+  std::memcpy(A, Ain, sizeof(A));
+  std::memcpy(b, bin, sizeof(b));
+  for (int l = 0; l < n; ++l) {
+    const int vs = m - l;
+    float vn = 0.f;
+    for (int i = 0; i < vs; ++i) { vl[i] = A[(l + i) * 6 + l]; vn += vl[i] * vl[i]; }
+    const float t0 = vl[0];
+    vl[0] = vl[0] + (vl[0] >= 0.f ? 1.f : -1.f) * std::sqrt(vn);
+    vn = std::sqrt(vn + vl[0] * vl[0] - t0 * t0);
+    for (int i = 0; i < vs; ++i) vl[i] /= vn;
+    for (int j = l; j < n; ++j) {
+      float va = 0.f;
+      for (int i = l; i < m; ++i) va += vl[i - l] * A[i * 6 + j];
+      for (int i = l; i < m; ++i) A[i * 6 + j] -= 2 * vl[i - l] * va;
+    }
+    hf[l] = vl[0] * vl[0];
+    for (int i = 1; i < vs; ++i) A[(l + i) * 6 + l] = vl[i] / vl[0];
+  }
+  for (int l = 0; l < n; ++l) {
+    vl[0] = 1.f;
+    for (int j = 1; j < m - l; ++j) vl[j] = A[(j + l) * 6 + l];
+    float vb = 0.f;
+    for (int i = l; i < m; ++i) vb += vl[i - l] * b[i];
+    for (int i = l; i < m; ++i) b[i] -= 2 * vl[i - l] * vb * hf[l];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    for (int j = n - 1; j > i; --j) b[i] -= b[j] * A[i * 6 + j];
+    if (std::fabs(A[i * 6 + i]) < eps) { std::memset(x, 0, 6 * sizeof(float)); return false; }
+    b[i] /= A[i * 6 + i];
+  }
+  std::memcpy(x, b, sizeof(b));
+  return true;
+}
+
+inline float cv_hypot(float a, float b) {
+  a = std::fabs(a); b = std::fabs(b);
+  if (a > b) { b /= a; return a * std::sqrt(1 + b * b); }
+  if (b > 0) { a /= b; return b * std::sqrt(1 + a * a); }
+  return 0.f;
+}
+
+// cv::eigen(A, E, V) for a symmetric CV_32F matrix -> JacobiImpl_<float>: largest off-diagonal pivot,
+// eigenvalues descending in W, eigenvectors as ROWS of V.
+inline void cv_eigen6(const float Ain[36], float W[6], float V[36]) {
+  const int n = 6;
+  const float eps = FLT_EPSILON;
+  float A[36];
+  std::memcpy(A, Ain, sizeof(A));
+  int indR[6], indC[6];
+  int i, j, k, m;
+  for (i = 0; i < n; ++i) { for (j = 0; j < n; ++j) V[i * 6 + j] = 0.f; V[i * 6 + i] = 1.f; }
+  float mv = 0.f;
+  for (k = 0; k < n; ++k) {
+    W[k] = A[7 * k];
+    if (k < n - 1) {
+      for (m = k + 1, mv = std::fabs(A[6 * k + m]), i = k + 2; i < n; ++i) {
+        const float val = std::fabs(A[6 * k + i]);
+        if (mv < val) mv = val, m = i;
+      }
+      indR[k] = m;
+    }
+    if (k > 0) {
+      for (m = 0, mv = std::fabs(A[k]), i = 1; i < k; ++i) {
+        const float val = std::fabs(A[6 * i + k]);
+        if (mv < val) mv = val, m = i;
+      }
+      indC[k] = m;
+    }
+  }
+  const int maxIters = n * n * 30;
+  for (int it = 0; it < maxIters; ++it) {
+    for (k = 0, mv = std::fabs(A[indR[0]]), i = 1; i < n - 1; ++i) {
+      const float val = std::fabs(A[6 * i + indR[i]]);
+      if (mv < val) mv = val, k = i;
+    }
+    int l = indR[k];
+    for (i = 1; i < n; ++i) {
+      const float val = std::fabs(A[6 * indC[i] + i]);
+      if (mv < val) mv = val, k = indC[i], l = i;
+    }
+    const float p = A[6 * k + l];
+    if (std::fabs(p) <= eps) break;
+    const float y = (float)((W[l] - W[k]) * 0.5);
+    float t = std::fabs(y) + cv_hypot(p, y);
+    float s = cv_hypot(p, t);
+    const float c = t / s;
+    s = p / s; t = (p / t) * p;
+    if (y < 0) s = -s, t = -t;
+    A[6 * k + l] = 0;
+    W[k] -= t;
+    W[l] += t;
+    float a0, b0;
+#define LIORF_ROT(v0, v1) a0 = v0, b0 = v1, v0 = a0 * c - b0 * s, v1 = a0 * s + b0 * c
+    for (i = 0; i < k; ++i) LIORF_ROT(A[6 * i + k], A[6 * i + l]);
+    for (i = k + 1; i < l; ++i) LIORF_ROT(A[6 * k + i], A[6 * i + l]);
+    for (i = l + 1; i < n; ++i) LIORF_ROT(A[6 * k + i], A[6 * l + i]);
+    for (i = 0; i < n; ++i) LIORF_ROT(V[6 * k + i], V[6 * l + i]);
+#undef LIORF_ROT
+    for (j = 0; j < 2; ++j) {
+      const int idx = j == 0 ? k : l;
+      if (idx < n - 1) {
+        for (m = idx + 1, mv = std::fabs(A[6 * idx + m]), i = idx + 2; i < n; ++i) {
+          const float val = std::fabs(A[6 * idx + i]);
+          if (mv < val) mv = val, m = i;
+        }
+        indR[idx] = m;
+      }
+      if (idx > 0) {
+        for (m = 0, mv = std::fabs(A[idx]), i = 1; i < idx; ++i) {
+          const float val = std::fabs(A[6 * i + idx]);
+          if (mv < val) mv = val, m = i;
+        }
+        indC[idx] = m;
+      }
+    }
+  }
+  for (k = 0; k < n - 1; ++k) {
+    m = k;
+    for (i = k + 1; i < n; ++i)
+      if (W[m] < W[i]) m = i;
+    if (k != m) {
+      std::swap(W[m], W[k]);
+      for (i = 0; i < n; ++i) std::swap(V[6 * m + i], V[6 * k + i]);
+    }
+  }
+}
+
+// Mat::inv() (DECOMP_LU) -> hal::LU32f -> LUImpl<float> on [A | I]: partial pivoting, eps = 10*FLT_EPSILON.
+inline bool cv_inv6(const float Ain[36], float inv[36]) {
+  const int m = 6;
+  const float eps = FLT_EPSILON * 10;
+  float A[36];
+  std::memcpy(A, Ain, sizeof(A));
+  float* b = inv;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) b[i * 6 + j] = i == j ? 1.f : 0.f;
+  for (int i = 0; i < m; ++i) {
+    int k = i;
+    for (int j = i + 1; j < m; ++j)
+      if (std::fabs(A[j * 6 + i]) > std::fabs(A[k * 6 + i])) k = j;
+    if (std::fabs(A[k * 6 + i]) < eps) { std::memset(inv, 0, 36 * sizeof(float)); return false; }
+    if (k != i) {
+      for (int j = i; j < m; ++j) std::swap(A[i * 6 + j], A[k * 6 + j]);
+      for (int j = 0; j < m; ++j) std::swap(b[i * 6 + j], b[k * 6 + j]);
+    }
+    const float d = -1 / A[i * 6 + i];
+    for (int j = i + 1; j < m; ++j) {
+      const float alpha = A[j * 6 + i] * d;
+      for (int c = i + 1; c < m; ++c) A[j * 6 + c] += alpha * A[i * 6 + c];
+      for (int c = 0; c < m; ++c) b[j * 6 + c] += alpha * b[i * 6 + c];
+    }
+  }
+  for (int i = m - 1; i >= 0; --i)
+    for (int j = 0; j < m; ++j) {
+      float s = b[i * 6 + j];
+      for (int k = i + 1; k < m; ++k) s -= A[i * 6 + k] * b[k * 6 + j];
+      b[i * 6 + j] = s / A[i * 6 + i];
+    }
+  return true;
+}
+
+// Mat * Mat for CV_32F (cv::gemm, small-matrix path GEMMSingleMul<float,double>): f64 accumulation
+// of exact f32 products, rounded once to f32.
+inline void cv_gemm6(const float A[36], const float B[36], float C[36]) {
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double s = 0;
+      for (int k = 0; k < 6; ++k) s += (double)A[i * 6 + k] * (double)B[k * 6 + j];
+      C[i * 6 + j] = (float)s;
+    }
+}
+inline void cv_gemv6(const float A[36], const float x[6], float y[6]) {
+  for (int i = 0; i < 6; ++i) {
+    double s = 0;
+    for (int k = 0; k < 6; ++k) s += (double)A[i * 6 + k] * (double)x[k];
+    y[i] = (float)s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9: Jacobian row of LMOptimization (MO:1714-1778) for one accepted correspondence.
+struct Trig { float srx, crx, sry, cry, srz, crz; };
+inline Trig lm_trig(const float pose[6]) {  // MO:1714-1719 (canonical f64 trig rounded to f32)
+  Trig t;
+  t.srx = (float)std::sin((double)pose[2]); t.crx = (float)std::cos((double)pose[2]);
+  t.sry = (float)std::sin((double)pose[1]); t.cry = (float)std::cos((double)pose[1]);
+  t.srz = (float)std::sin((double)pose[0]); t.crz = (float)std::cos((double)pose[0]);
+  return t;
+}
+inline void jacobian_row(const Trig& g, const P4& o, const P4& c, float row[6], float& rhs) {
+  const float srx = g.srx, crx = g.crx, sry = g.sry, cry = g.cry, srz = g.srz, crz = g.crz;
+  const float arx = (-srx * cry * o.x - (srx * sry * srz + crx * crz) * o.y + (crx * srz - srx * sry * crz) * o.z) * c.x
+                  + (crx * cry * o.x - (srx * crz - crx * sry * srz) * o.y + (crx * sry * crz + srx * srz) * o.z) * c.y;
+  const float ary = (-crx * sry * o.x + crx * cry * srz * o.y + crx * cry * crz * o.z) * c.x
+                  + (-srx * sry * o.x + srx * sry * srz * o.y + srx * cry * crz * o.z) * c.y
+                  + (-cry * o.x - sry * srz * o.y - sry * crz * o.z) * c.z;
+  const float arz = ((crx * sry * crz + srx * srz) * o.y + (srx * crz - crx * sry * srz) * o.z) * c.x
+                  + ((-crx * srz + srx * sry * crz) * o.y + (-srx * sry * srz - crx * crz) * o.z) * c.y
+                  + (cry * crz * o.y - cry * srz * o.z) * c.z;
+  row[0] = arz; row[1] = ary; row[2] = arx; row[3] = c.x; row[4] = c.y; row[5] = c.z;
+  rhs = -c.i;
+}
+
+// a9: everything in LMOptimization after AtA/AtB exist (MO:1784-1835).  Returns true if converged.
+struct LmState {
+  float pose[6];
+  float matP[36];
+  int degenerate;
+};
+inline bool lm_solve_update(const double JtJ[36], const double Jtr[6], int iterCount, LmState& st,
+                            float& deltaR, float& deltaT) {
+  float AtA[36], AtB[6], X[6];
+  for (int i = 0; i < 36; ++i) AtA[i] = (float)JtJ[i];
+  for (int i = 0; i < 6; ++i) AtB[i] = (float)Jtr[i];
+  cv_solve6_qr(AtA, AtB, X);
+  if (iterCount == 0) {
+    float E[6], V[36], V2[36], Vi[36];
+    cv_eigen6(AtA, E, V);
+    std::memcpy(V2, V, sizeof(V));
+    st.degenerate = 0;
+    for (int i = 5; i >= 0; --i) {
+      if (E[i] < 100.f) {
+        for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f;
+        st.degenerate = 1;
+      } else break;
+    }
+    cv_inv6(V, Vi);
+    cv_gemm6(Vi, V2, st.matP);
+  }
+  if (st.degenerate) {
+    float X2[6];
+    std::memcpy(X2, X, sizeof(X));
+    cv_gemv6(st.matP, X2, X);
+  }
+  for (int i = 0; i < 6; ++i) st.pose[i] += X[i];
+  // MO:1824-1831: pcl::rad2deg(float) is a float multiply by 180/M_PI evaluated... see note in DESIGN
+  const double r2d = 180.0 / M_PI;
+  const float rx = (float)(X[0] * (float)r2d), ry = (float)(X[1] * (float)r2d), rz = (float)(X[2] * (float)r2d);
+  deltaR = (float)std::sqrt((double)rx * rx + (double)ry * ry + (double)rz * rz);
+  const float tx = X[3] * 100, ty = X[4] * 100, tz = X[5] * 100;
+  deltaT = (float)std::sqrt((double)tx * tx + (double)ty * ty + (double)tz * tz);
+  return (double)deltaR < 0.05 && (double)deltaT < 0.05;
+}
+
+}  // namespace liorf_oracle
