@@ -59,7 +59,9 @@ typedef struct liogpu_params {
   float lidar_max_range;     /* UT:284, IP:598                                                   */
   float lidar_max_intensity; /* UT:285, IP:598                                                   */
   float knn_cell_size;       /* edge of the sorted-grid cell used for the 5-NN index; 0 = auto   */
-  int reserved[7];
+  float knn_phase1_radius;   /* radius of the cheap first search phase; 0 = auto (2 x map leaf),
+                                < 0 = single phase.  Tuning only: results do not depend on it.   */
+  int reserved[6];
 } liogpu_params;
 
 /* Result block of liogpu_scan2map (everything the reference keeps in members after the loop). */

@@ -141,7 +141,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
+                    &c.fail_buf, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
   for (DevBuf* b : bufs) b->release();
   for (auto& kv : c.keyframes) kv.second.first.release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -322,7 +322,7 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   bool overflow = false;
   rc = voxel_downsample_dev(c, c->map_raw4.as<float4>(), (int)total, leaf, c->map4, &m, &overflow);
   if (rc) return rc;
-  rc = grid_build_dev(c, c->map4.as<float4>(), m);
+  rc = grid_build_dev(c, c->map4.as<float4>(), m, leaf);
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_map = m;
@@ -344,7 +344,7 @@ int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
   rc = load_cloud(c, xyzi, n, stride, c->map4);
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  rc = grid_build_dev(c, c->map4.as<float4>(), n);
+  rc = grid_build_dev(c, c->map4.as<float4>(), n, c->prm.surrounding_keyframe_map_leaf_size);
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -57,10 +57,13 @@ struct GridParams {
   int n_points;
   unsigned n_cells;
   float gate_d2;      // squared search radius (1.0 for surfOptimization, MO:1641)
+  float gate1_d2;     // squared radius of the cheap first search phase (>= gate_d2 disables it)
 };
 
 // ---- state of the LM loop kept on device between iterations (MO:171,176,177) ----
 struct LmDevState {
+  float T[12];     // transPointAssociateToMap of `pose` (MO:1615), refreshed after every pose update
+  float trig[6];   // srx, crx, sry, cry, srz, crz of `pose` (MO:1714-1719)
   float pose[6];
   float matP[36];
   int degenerate;
@@ -100,7 +103,7 @@ struct Ctx {
   // sort + scan scratch
   DevBuf keys0, keys1, vals0, vals1, counters, scan_tmp, seg_flag, seg_start;
   // small device structs
-  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc;
+  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf;
   // per-point debug outputs of surf_optimization
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
   // pinned host mirrors
@@ -132,7 +135,7 @@ cudaError_t exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, int n,
 cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm);
 int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& out, int* n_out, bool* overflow);
 // --- grid.cu
-int grid_build_dev(Ctx* c, const float4* map4, int n);
+int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint);
 // --- s2m.cu
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info);

@@ -19,8 +19,8 @@ __device__ __forceinline__ float ord2f_g(unsigned o) {
 }
 
 // mm = output of vox_minmax_kernel (ordered-uint min[3], max[3], finite count)
-__global__ void grid_setup_kernel(const unsigned* __restrict__ mm, float cell, float gate_d2, unsigned max_cells,
-                                  GridParams* __restrict__ gp) {
+__global__ void grid_setup_kernel(const unsigned* __restrict__ mm, float cell, float gate_d2, float gate1_d2,
+                                  unsigned max_cells, GridParams* __restrict__ gp) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   GridParams g;
   g.n_points = (int)mm[6];
@@ -51,6 +51,7 @@ __global__ void grid_setup_kernel(const unsigned* __restrict__ mm, float cell, f
   // the largest coordinate), so a pruned cell can never hold a point that ties or beats the worst.
   g.slack = maxabs * 9.5367431640625e-07f;  // 2^-20
   g.gate_d2 = gate_d2;
+  g.gate1_d2 = gate1_d2;
   *gp = g;
 }
 
@@ -90,7 +91,7 @@ grid_gather_kernel(const float4* __restrict__ map4, const uint32_t* __restrict__
   map_sorted[j] = make_float4(p.x, p.y, p.z, __int_as_float((int)src));
 }
 
-int grid_build_dev(Ctx* c, const float4* map4, int n) {
+int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
   c->grid_valid = false;
   c->n_map = n;
   if (n <= 0) return LIOGPU_OK;
@@ -104,8 +105,17 @@ int grid_build_dev(Ctx* c, const float4* map4, int n) {
   unsigned* mm = c->minmax.as<unsigned>();
   GridParams* d_gp = c->grid_setup.as<GridParams>();
   LIOGPU_CUDA_OK(c, launch_minmax(c, map4, n, mm));
-  const float cell = c->prm.knn_cell_size > 0.f ? c->prm.knn_cell_size : 0.5f;
-  grid_setup_kernel<<<1, 32, 0, c->stream>>>(mm, cell, 1.0f, 1u << 25, d_gp);
+  // Tuning (results never depend on it): the first search phase looks inside r1 ~ twice the map's point
+  // spacing (the VoxelGrid leaf), where a query on a mapped surface already finds its 5 neighbours; the
+  // cell edge follows r1 so that phase 1 touches a 3x3x3 block of cells.
+  const float gate_d2 = 1.0f;  // mapOptmization.cpp:1641
+  const float spacing = leaf_hint > 0.f ? leaf_hint : 0.2f;
+  float r1 = c->prm.knn_phase1_radius > 0.f ? c->prm.knn_phase1_radius : 2.0f * spacing;
+  float gate1_d2 = r1 * r1;
+  if (c->prm.knn_phase1_radius < 0.f || gate1_d2 >= 0.64f * gate_d2) gate1_d2 = gate_d2;  // single phase
+  float cell = c->prm.knn_cell_size;
+  if (!(cell > 0.f)) cell = fminf(fmaxf(r1, 0.25f), 0.5f);
+  grid_setup_kernel<<<1, 32, 0, c->stream>>>(mm, cell, gate_d2, gate1_d2, 1u << 25, d_gp);
   c->launches += 1;
   GridParams* h_gp = reinterpret_cast<GridParams*>((char*)c->h_pinned + 2048);
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, c->stream));

@@ -23,7 +23,13 @@
 
 namespace liogpu {
 
-constexpr int S2M_THREADS = 256;
+#ifndef S2M_THREADS_CFG
+#define S2M_THREADS_CFG 256
+#endif
+#ifndef S2M_MINBLOCKS_CFG
+#define S2M_MINBLOCKS_CFG 3
+#endif
+constexpr int S2M_THREADS = S2M_THREADS_CFG;
 constexpr int S2M_SUMS = 32;  // 21 (upper AtA) + 6 (AtB) + nsel + ties, padded to 32
 
 struct SurfDebugOut {
@@ -34,186 +40,612 @@ struct SurfDebugOut {
   unsigned char* tie;   // n
 };
 
-#define LIOGPU_LT(da, ia, db, ib) ((da) < (db) || ((da) == (db) && (ia) < (ib)))
-
+// Running 5 best (d2, map index) pairs as 64-bit keys: (bits of d2) << 32 | index.  d2 >= +0 so the
+// bit pattern orders like the value, and the low word breaks ties toward the lower map index — one
+// unsigned 64-bit compare per test, branch-free compare-exchange bubble on insertion.
+typedef unsigned long long u64;
 struct Top5 {
-  float d0, d1, d2, d3, d4;
-  int i0, i1, i2, i3, i4;
-  float rej;  // best distance among candidates that are not in the top 5 (tie logging)
+  u64 k0, k1, k2, k3, k4;
+  float rej;  // best distance among candidates that did not stay in the top 5 (tie logging)
   __device__ __forceinline__ void init(float gate) {
-    d0 = d1 = d2 = d3 = d4 = gate;
-    i0 = i1 = i2 = i3 = i4 = -1;
+    // sentinel (gate, index 0): a candidate at exactly the gate distance never compares below it
+    k0 = k1 = k2 = k3 = k4 = ((u64)__float_as_uint(gate)) << 32;
     rej = FLT_MAX;
   }
   __device__ __forceinline__ void offer(float d, int id) {
-    if (LIOGPU_LT(d, id, d4, i4)) {
-      rej = fminf(rej, d4);
-      d4 = d; i4 = id;
-      if (LIOGPU_LT(d4, i4, d3, i3)) {
-        swapf(d3, d4); swapi(i3, i4);
-        if (LIOGPU_LT(d3, i3, d2, i2)) {
-          swapf(d2, d3); swapi(i2, i3);
-          if (LIOGPU_LT(d2, i2, d1, i1)) {
-            swapf(d1, d2); swapi(i1, i2);
-            if (LIOGPU_LT(d1, i1, d0, i0)) { swapf(d0, d1); swapi(i0, i1); }
-          }
-        }
-      }
+    const u64 key = (((u64)__float_as_uint(d)) << 32) | (u64)(unsigned)id;
+    if (key < k4) {
+      rej = fminf(rej, __uint_as_float((unsigned)(k4 >> 32)));
+      u64 lo;
+      k4 = key;
+      lo = min(k3, k4); k4 = max(k3, k4); k3 = lo;
+      lo = min(k2, k3); k3 = max(k2, k3); k2 = lo;
+      lo = min(k1, k2); k2 = max(k1, k2); k1 = lo;
+      lo = min(k0, k1); k1 = max(k0, k1); k0 = lo;
     } else {
       rej = fminf(rej, d);
     }
   }
+  __device__ __forceinline__ float d(const u64 k) const { return __uint_as_float((unsigned)(k >> 32)); }
+  __device__ __forceinline__ int i(const u64 k) const { return (int)(unsigned)(k & 0xffffffffull); }
+  __device__ __forceinline__ bool tie() const {
+    return d(k0) == d(k1) || d(k1) == d(k2) || d(k2) == d(k3) || d(k3) == d(k4) || d(k4) == rej;
+  }
 };
 
-// Exact 5 nearest map points of q within sqrt(gate_d2), ascending (d2, map index).
-__device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, const float4* __restrict__ map_sorted,
+// FLANN L2_Simple<float>: result = 0; result += diff*diff for x, y, z — f32, no FMA (-fmad=false)
+__device__ __forceinline__ float l2_simple(const float4 q, const float4 p) {
+  float d = q.x - p.x;
+  float acc = d * d;
+  d = q.y - p.y; acc = acc + d * d;
+  d = q.z - p.z; acc = acc + d * d;
+  return acc;
+}
+
+__device__ __forceinline__ int zigzag(int k) { return (k & 1) ? -((k + 1) >> 1) : (k >> 1); }  // 0,-1,+1,-2,+2,...
+
+// Exact 5 nearest map points of q among those closer than sqrt(gate_d2), ascending (d2, map index).
+// On return t.d(t.k4) < gate_d2 iff at least 5 such points exist (then the answer is exact).
+__device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, const float gate_d2,
+                                          const float4* __restrict__ map_sorted,
                                           const uint32_t* __restrict__ cell_start, Top5& t) {
-  t.init(g.gate_d2);
+  t.init(gate_d2);
   const float s2 = 2.0f * g.slack;
-  const float reach = sqrtf(g.gate_d2) + s2;
-  const int R = (int)ceilf(reach * g.inv_h);
-  const int cz = (int)floorf((q.z - g.oz) * g.inv_h);
-  const int cy = (int)floorf((q.y - g.oy) * g.inv_h);
-  for (int kz = 0; kz <= 2 * R; ++kz) {
-    const int dz = (kz & 1) ? -((kz + 1) >> 1) : (kz >> 1);  // 0,-1,+1,-2,+2,...
-    const int z = cz + dz;
-    if (z < 0 || z >= g.nz) continue;
+  const float reach = sqrtf(gate_d2) * 1.000001f + s2;
+  int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
+  int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
+  zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
+  ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
+  if (zmin > zmax || ymin > ymax) return;
+  const int cz = min(max((int)floorf((q.z - g.oz) * g.inv_h), zmin), zmax);
+  const int cy = min(max((int)floorf((q.y - g.oy) * g.inv_h), ymin), ymax);
+  const int nzs = zmax - zmin + 1, nys = ymax - ymin + 1;
+  for (int kz = 0, seen_z = 0; seen_z < nzs; ++kz) {  // centre-out over the z slabs in reach
+    const int z = cz + zigzag(kz);
+    if (z < zmin || z > zmax) continue;
+    ++seen_z;
     const float zlo = g.oz + (float)z * g.h;
-    float gz = fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2;
-    gz = fmaxf(gz, 0.f);
+    const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
     const float gz2 = gz * gz;
-    if (gz2 > t.d4) continue;
-    for (int ky = 0; ky <= 2 * R; ++ky) {
-      const int dy = (ky & 1) ? -((ky + 1) >> 1) : (ky >> 1);
-      const int y = cy + dy;
-      if (y < 0 || y >= g.ny) continue;
+    if (gz2 > t.d(t.k4)) continue;
+    for (int ky = 0, seen_y = 0; seen_y < nys; ++ky) {
+      const int y = cy + zigzag(ky);
+      if (y < ymin || y > ymax) continue;
+      ++seen_y;
       const float ylo = g.oy + (float)y * g.h;
-      float gy = fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2;
-      gy = fmaxf(gy, 0.f);
+      const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
       const float m2 = (gz2 + gy * gy) * 0.999999f;
-      if (m2 > t.d4) continue;
-      const float r = sqrtf(t.d4 - m2) * 1.000001f + s2;
+      const float worst = t.d(t.k4);
+      if (m2 > worst) continue;
+      const float r = sqrtf(worst - m2) * 1.000001f + s2;
       int xlo = (int)floorf((q.x - r - g.ox) * g.inv_h);
       int xhi = (int)floorf((q.x + r - g.ox) * g.inv_h);
-      xlo = xlo < 0 ? 0 : xlo;
-      xhi = xhi >= g.nx ? g.nx - 1 : xhi;
+      xlo = max(xlo, 0);
+      xhi = min(xhi, g.nx - 1);
       if (xlo > xhi) continue;
       const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
       const uint32_t s = __ldg(cell_start + row + xlo);
       const uint32_t e = __ldg(cell_start + row + xhi + 1);
-      for (uint32_t j = s; j < e; ++j) {
-        const float4 p = __ldg(map_sorted + j);
-        float d = q.x - p.x;
-        float acc = d * d;            // FLANN L2_Simple: result = 0; result += diff*diff (x, y, z)
-        d = q.y - p.y; acc = acc + d * d;
-        d = q.z - p.z; acc = acc + d * d;
-        t.offer(acc, __float_as_int(p.w));
+      for (uint32_t j = s; j < e; j += 4) {
+        // four independent 16-byte loads in flight per thread (clamped, so no predicate on the loads)
+        const uint32_t last = e - 1;
+        const float4 p0 = __ldg(map_sorted + j);
+        const float4 p1 = __ldg(map_sorted + min(j + 1, last));
+        const float4 p2 = __ldg(map_sorted + min(j + 2, last));
+        const float4 p3 = __ldg(map_sorted + min(j + 3, last));
+        t.offer(l2_simple(q, p0), __float_as_int(p0.w));
+        if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
+        if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
+        if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
       }
     }
   }
 }
 
-// ---- the 6x6 tail of LMOptimization, one thread (mapOptmization.cpp:1721-1835) ----
-__device__ __noinline__ void lm_finalize(LmDevState* st, const double* sums) {
+__device__ __forceinline__ u64 warp_min_u64(const u64 v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return ((u64)mhi << 32) | (u64)mlo;
+}
+
+// Warp-cooperative exact 5-NN of ONE query inside the full gate (phase 2: the few queries whose
+// neighbours are not within the phase-1 radius).  Lanes take the (y,z) rows in reach, 32 at a time: all
+// the cell_start look-ups are in flight together; the rows' candidates are then flattened with a warp
+// prefix sum and handed out one per lane, so the candidate loads are in flight together too.  Each lane
+// keeps the best 5 of the candidates it saw; the lanes' lists are merged with five warp-wide minima.
+// The result is identical to the sequential search: a set selection under the total order (d2, index).
+__device__ __forceinline__ void warp_knn5(const float4 q, const GridParams& g, const float4* __restrict__ map_sorted,
+                                          const uint32_t* __restrict__ cell_start, const int lane, Top5& out) {
+  Top5 t;
+  t.init(g.gate_d2);
+  out.init(g.gate_d2);
+  const float s2 = 2.0f * g.slack;
+  const float reach = sqrtf(g.gate_d2) * 1.000001f + s2;
+  int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
+  int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
+  zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
+  ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
+  if (zmin > zmax || ymin > ymax) return;
+  const int nys = ymax - ymin + 1;
+  const int nrows = (zmax - zmin + 1) * nys;
+  for (int base = 0; base < nrows; base += 32) {
+    const int r = base + lane;
+    uint32_t s = 0, cnt = 0;
+    if (r < nrows) {
+      const int z = zmin + r / nys, y = ymin + r % nys;
+      const float zlo = g.oz + (float)z * g.h, ylo = g.oy + (float)y * g.h;
+      const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
+      const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
+      const float m2 = (gz * gz + gy * gy) * 0.999999f;
+      if (m2 <= g.gate_d2) {
+        const float rr = sqrtf(g.gate_d2 - m2) * 1.000001f + s2;
+        int xlo = (int)floorf((q.x - rr - g.ox) * g.inv_h);
+        int xhi = (int)floorf((q.x + rr - g.ox) * g.inv_h);
+        xlo = max(xlo, 0);
+        xhi = min(xhi, g.nx - 1);
+        if (xlo <= xhi) {
+          const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+          s = __ldg(cell_start + row + xlo);
+          cnt = __ldg(cell_start + row + xhi + 1) - s;
+        }
+      }
+    }
+    uint32_t incl = cnt;  // inclusive prefix sum of the rows' candidate counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      // owner row of candidate c: the first lane whose inclusive sum exceeds c (binary search by shuffles)
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+        if (v <= c) lo += step;
+      }
+      lo = min(lo, 31);
+      const uint32_t row_s = __shfl_sync(0xffffffffu, s, lo);
+      const uint32_t row_incl = __shfl_sync(0xffffffffu, incl, lo);
+      const uint32_t row_cnt = __shfl_sync(0xffffffffu, cnt, lo);
+      if (c < total) {
+        const uint32_t j = row_s + (c - (row_incl - row_cnt));
+        const float4 p = __ldg(map_sorted + j);
+        t.offer(l2_simple(q, p), __float_as_int(p.w));
+      }
+    }
+  }
+  // merge: five times take the smallest head over the lanes and pop it from its owner's list
+  u64 res[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const u64 m = warp_min_u64(t.k0);
+    res[k] = m;
+    const unsigned owners = __ballot_sync(0xffffffffu, t.k0 == m);
+    if (lane == __ffs(owners) - 1) {
+      t.rej = fminf(t.rej, FLT_MAX);
+      t.k0 = t.k1; t.k1 = t.k2; t.k2 = t.k3; t.k3 = t.k4; t.k4 = ~0ull;
+    }
+  }
+  // best candidate that is NOT in the result (tie logging): a remaining head or something a lane dropped
+  const u64 next = warp_min_u64(t.k0);
+  float rj = fminf(t.rej, next == ~0ull ? FLT_MAX : __uint_as_float((unsigned)(next >> 32)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rj = fminf(rj, __shfl_xor_sync(0xffffffffu, rj, o));
+  out.k0 = res[0]; out.k1 = res[1]; out.k2 = res[2]; out.k3 = res[3]; out.k4 = res[4];
+  out.rej = rj;
+}
+
+// ---- the 6x6 tail of LMOptimization (mapOptmization.cpp:1721-1835), executed by ONE WARP ----
+// A single thread walking these 6x6 routines through local memory cost ~90 us per iteration (~170 us on
+// iteration 0) — more than the search itself.  Here the matrices live in shared memory and the lanes
+// take independent elements (columns of the Householder update, Jacobi rotation indices, columns of the
+// LU elimination), while every individual element still sees exactly the operation sequence of the
+// sequential OpenCV routine restated in pose_math.cuh — so the results stay bit-identical to it.
+struct FinSmem {
+  float AtA[36], AtB[6], X[6];
+  float QA[36], qb[6], vl[6], hf[6];
+  float JA[36], W[6], V[36], V2[36], Vi[36];
+  int indR[6], indC[6];
+};
+constexpr unsigned FULL = 0xffffffffu;
+
+// cv::solve(AtA, AtB, X, DECOMP_QR) (:1784) — hal::QR32f Householder.  Lane j owns column j.
+__device__ __forceinline__ void warp_solve6_qr(FinSmem& m, const int lane) {
+  for (int e = lane; e < 36; e += 32) m.QA[e] = m.AtA[e];
+  if (lane < 6) m.qb[lane] = m.AtB[lane];
+  __syncwarp();
+  for (int l = 0; l < 6; ++l) {
+    const int vs = 6 - l;
+    float v = lane < vs ? m.QA[(l + lane) * 6 + l] : 0.f;
+    const float sq = v * v;
+    float vn = 0.f;
+    for (int i = 0; i < vs; ++i) vn += __shfl_sync(FULL, sq, i);  // sequential order of the reference
+    const float t0 = __shfl_sync(FULL, v, 0);
+    const float v0 = t0 + (t0 >= 0.f ? 1.f : -1.f) * sqrtf(vn);
+    const float vn2 = sqrtf(vn + v0 * v0 - t0 * t0);
+    if (lane == 0) v = v0;
+    v = v / vn2;
+    if (lane < vs) m.vl[lane] = v;
+    __syncwarp();
+    if (lane >= l && lane < 6) {  // column j = lane
+      float va = 0.f;
+      for (int i = l; i < 6; ++i) va += m.vl[i - l] * m.QA[i * 6 + lane];
+      for (int i = l; i < 6; ++i) m.QA[i * 6 + lane] -= 2 * m.vl[i - l] * va;
+    }
+    __syncwarp();
+    if (lane == 0) m.hf[l] = m.vl[0] * m.vl[0];
+    if (lane >= 1 && lane < vs) m.QA[(l + lane) * 6 + l] = m.vl[lane] / m.vl[0];
+    __syncwarp();
+  }
+  for (int l = 0; l < 6; ++l) {
+    float vb = 0.f;
+    for (int i = l; i < 6; ++i) vb += (i == l ? 1.f : m.QA[i * 6 + l]) * m.qb[i];
+    __syncwarp();
+    if (lane >= l && lane < 6) m.qb[lane] -= 2 * (lane == l ? 1.f : m.QA[lane * 6 + l]) * vb * m.hf[l];
+    __syncwarp();
+  }
+  if (lane == 0) {
+    bool ok = true;
+    for (int i = 5; i >= 0 && ok; --i) {
+      for (int j = 5; j > i; --j) m.qb[i] -= m.qb[j] * m.QA[i * 6 + j];
+      if (fabsf(m.QA[i * 6 + i]) < FLT_EPSILON * 10) { ok = false; break; }
+      m.qb[i] /= m.QA[i * 6 + i];
+    }
+    for (int i = 0; i < 6; ++i) m.X[i] = ok ? m.qb[i] : 0.f;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int jacobi_argmax_row(const float* A, int idx) {  // indR[idx]: first max of |A[idx][idx+1..5]|
+  int mI = idx + 1;
+  float mv = fabsf(A[6 * idx + mI]);
+  for (int i = idx + 2; i < 6; ++i) {
+    const float val = fabsf(A[6 * idx + i]);
+    if (mv < val) { mv = val; mI = i; }
+  }
+  return mI;
+}
+__device__ __forceinline__ int jacobi_argmax_col(const float* A, int idx) {  // indC[idx]: first max of |A[0..idx-1][idx]|
+  int mI = 0;
+  float mv = fabsf(A[idx]);
+  for (int i = 1; i < idx; ++i) {
+    const float val = fabsf(A[6 * i + idx]);
+    if (mv < val) { mv = val; mI = i; }
+  }
+  return mI;
+}
+
+// cv::eigen(matAtA, matE, matV) (:1792) — JacobiImpl_<float>: W descending, eigenvectors as rows of V.
+__device__ __forceinline__ void warp_eigen6(FinSmem& m, const int lane) {
+  for (int e = lane; e < 36; e += 32) { m.JA[e] = m.AtA[e]; m.V[e] = (e / 6 == e % 6) ? 1.f : 0.f; }
+  __syncwarp();
+  if (lane < 6) {
+    m.W[lane] = m.JA[7 * lane];
+    if (lane < 5) m.indR[lane] = jacobi_argmax_row(m.JA, lane);
+    if (lane > 0) m.indC[lane] = jacobi_argmax_col(m.JA, lane);
+  }
+  __syncwarp();
+  for (int it = 0; it < 6 * 6 * 30; ++it) {
+    // pivot: first strict maximum over |A[i][indR[i]]| (i=0..4) then |A[indC[i]][i]| (i=1..5)
+    float cand = -1.f;
+    if (lane < 5) cand = fabsf(m.JA[6 * lane + m.indR[lane]]);
+    else if (lane < 10) cand = fabsf(m.JA[6 * m.indC[lane - 4] + (lane - 4)]);
+    const int cb = __float_as_int(cand);
+    const int mb = __reduce_max_sync(FULL, cb);
+    const int pl = __ffs(__ballot_sync(FULL, cb == mb)) - 1;
+    int k, l;
+    if (pl < 5) { k = pl; l = m.indR[k]; } else { l = pl - 4; k = m.indC[l]; }
+    const float p = m.JA[6 * k + l];
+    if (fabsf(p) <= FLT_EPSILON) break;
+    const float y = (float)((m.W[l] - m.W[k]) * 0.5);
+    float t = fabsf(y) + cv_hypotf(p, y);
+    float s = cv_hypotf(p, t);
+    const float c = t / s;
+    s = p / s;
+    t = (p / t) * p;
+    if (y < 0) { s = -s; t = -t; }
+    __syncwarp();
+    if (lane == 0) { m.JA[6 * k + l] = 0; m.W[k] -= t; m.W[l] += t; }
+    if (lane < 6 && lane != k && lane != l) {  // rotate rows and columns k and l of the upper triangle
+      const int i = lane;
+      const int r0 = i < k ? 6 * i + k : 6 * k + i;
+      const int r1 = i < l ? 6 * i + l : 6 * l + i;
+      const float a0 = m.JA[r0], b0 = m.JA[r1];
+      m.JA[r0] = a0 * c - b0 * s;
+      m.JA[r1] = a0 * s + b0 * c;
+    } else if (lane >= 8 && lane < 14) {        // rotate the eigenvectors
+      const int i = lane - 8;
+      const float a0 = m.V[6 * k + i], b0 = m.V[6 * l + i];
+      m.V[6 * k + i] = a0 * c - b0 * s;
+      m.V[6 * l + i] = a0 * s + b0 * c;
+    }
+    __syncwarp();
+    if (lane == 0 && k < 5) m.indR[k] = jacobi_argmax_row(m.JA, k);
+    if (lane == 1 && k > 0) m.indC[k] = jacobi_argmax_col(m.JA, k);
+    if (lane == 2 && l < 5) m.indR[l] = jacobi_argmax_row(m.JA, l);
+    if (lane == 3 && l > 0) m.indC[l] = jacobi_argmax_col(m.JA, l);
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int k = 0; k < 5; ++k) {  // sort eigenvalues (descending) and eigenvectors
+    int mI = k;
+    for (int i = k + 1; i < 6; ++i)
+      if (m.W[mI] < m.W[i]) mI = i;
+    __syncwarp();
+    if (k != mI) {
+      if (lane == 0) { const float tw = m.W[mI]; m.W[mI] = m.W[k]; m.W[k] = tw; }
+      if (lane >= 8 && lane < 14) {
+        const int i = lane - 8;
+        const float tv = m.V[6 * mI + i]; m.V[6 * mI + i] = m.V[6 * k + i]; m.V[6 * k + i] = tv;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// matV.inv() (:1807) — cv::invert DECOMP_LU = hal::LU32f on [V | I].  Lane c < 6 owns column c of V,
+// lane 6 + c owns column c of the right-hand side; row operations are identical on every column.
+__device__ __forceinline__ void warp_inv6_lu(FinSmem& m, const int lane) {
+  float x[6];
+  const bool isA = lane < 6, isB = lane >= 6 && lane < 12;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) x[r] = isA ? m.V[r * 6 + lane] : ((isB && r == lane - 6) ? 1.f : 0.f);
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    int k = i;  // pivot: first row with the largest |A[j][i]|, j >= i (computed by the owner of column i)
+    float best = fabsf(x[i]);
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      const float v = fabsf(x[j]);
+      if (v > best) { best = v; k = j; }
+    }
+    k = __shfl_sync(FULL, k, i);
+    best = __shfl_sync(FULL, best, i);
+    if (best < FLT_EPSILON * 10) { ok = false; break; }
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j)
+      if (k == j) { const float tv = x[i]; x[i] = x[j]; x[j] = tv; }
+    const float d = -1 / __shfl_sync(FULL, x[i], i);
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      const float alpha = __shfl_sync(FULL, x[j], i) * d;
+      if (lane != i) x[j] += alpha * x[i];  // column i itself is left as LUImpl leaves it (never read again)
+    }
+  }
+  if (ok) {
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+      float sacc = x[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) {
+        const float aik = __shfl_sync(FULL, x[i], k);  // A[i][k] lives in lane k
+        sacc -= aik * x[k];
+      }
+      const float aii = __shfl_sync(FULL, x[i], i);
+      if (isB) x[i] = sacc / aii;
+    }
+  }
+  if (isB) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) m.Vi[r * 6 + (lane - 6)] = ok ? x[r] : 0.f;
+  }
+  __syncwarp();
+}
+
+// transPointAssociateToMap and the LM trig terms of the current pose, computed ONCE per iteration
+// instead of once per thread block; lanes 0-2 evaluate the f64 sin/cos of roll, pitch, yaw in parallel.
+__device__ __forceinline__ void warp_refresh_transform(LmDevState* st, const int lane) {
+  float sn = 0.f, cs = 0.f;
+  if (lane < 3) {
+    const double a = (double)st->pose[lane];
+    sn = (float)sin(a);
+    cs = (float)cos(a);
+  }
+  const float F = __shfl_sync(FULL, sn, 0), E = __shfl_sync(FULL, cs, 0);  // roll
+  const float D = __shfl_sync(FULL, sn, 1), C = __shfl_sync(FULL, cs, 1);  // pitch
+  const float B = __shfl_sync(FULL, sn, 2), A = __shfl_sync(FULL, cs, 2);  // yaw
+  if (lane == 0) {  // pcl::getTransformation — same products as pose_to_T
+    const float DE = D * E, DF = D * F;
+    float* T = st->T;
+    T[0] = A * C;  T[1] = A * DF - B * E;  T[2] = B * F + A * DE;  T[3] = st->pose[3];
+    T[4] = B * C;  T[5] = A * E + B * DF;  T[6] = B * DE - A * F;  T[7] = st->pose[4];
+    T[8] = -D;     T[9] = C * F;           T[10] = C * E;          T[11] = st->pose[5];
+    // srx,crx = sin,cos(yaw); sry,cry = (pitch); srz,crz = (roll)  (:1714-1719)
+    st->trig[0] = B; st->trig[1] = A; st->trig[2] = D; st->trig[3] = C; st->trig[4] = F; st->trig[5] = E;
+  }
+}
+__global__ void lm_prepare_kernel(LmDevState* st) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) warp_refresh_transform(st, threadIdx.x);
+}
+
+__device__ __noinline__ void lm_finalize_warp(LmDevState* st, const double* sums, FinSmem& m, const int lane) {
   const int it = st->iter;
   const int nsel = (int)sums[27];
-  st->n_sel = nsel;
-  st->tie_queries = (int)sums[28];
-  st->nsel_hist[it] = nsel;
   // expand the upper triangle; AtA(a,b) and AtA(b,a) are the same f64 sum of the same products
-  int p = 0;
-  for (int a = 0; a < 6; ++a)
-    for (int b = a; b < 6; ++b) {
-      st->JtJ[a * 6 + b] = sums[p];
-      st->JtJ[b * 6 + a] = sums[p];
-      ++p;
-    }
-  for (int a = 0; a < 6; ++a) st->Jtr[a] = sums[21 + a];
+  for (int e = lane; e < 36; e += 32) {
+    int a = e / 6, b = e % 6;
+    if (a > b) { const int tt = a; a = b; b = tt; }
+    const double v = sums[a * 6 - (a * (a - 1)) / 2 + (b - a)];
+    st->JtJ[e] = v;
+    m.AtA[e] = (float)v;
+  }
+  if (lane < 6) { st->Jtr[lane] = sums[21 + lane]; m.AtB[lane] = (float)sums[21 + lane]; }
+  if (lane == 0) { st->n_sel = nsel; st->tie_queries = (int)sums[28]; st->nsel_hist[it] = nsel; }
+  __syncwarp();
   bool conv = false;
   if (nsel >= 50) {  // :1721-1724 — below 50 the pose is untouched and the loop just repeats
-    float AtA[36], AtB[6], X[6];
-    for (int i = 0; i < 36; ++i) AtA[i] = (float)st->JtJ[i];
-    for (int i = 0; i < 6; ++i) AtB[i] = (float)st->Jtr[i];
-    solve6_qr(AtA, AtB, X);
+    warp_solve6_qr(m, lane);
     if (it == 0) {  // :1786-1808
-      float E[6], V[36], V2[36], Vi[36];
-      eigen6_jacobi(AtA, E, V);
-      for (int i = 0; i < 36; ++i) V2[i] = V[i];
-      int deg = 0;
-      for (int i = 5; i >= 0; --i) {
-        if (E[i] < 100.f) {
-          for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f;
-          deg = 1;
-        } else {
-          break;
+      warp_eigen6(m, lane);
+      for (int e = lane; e < 36; e += 32) m.V2[e] = m.V[e];
+      __syncwarp();
+      if (lane == 0) {
+        int deg = 0;
+        for (int i = 5; i >= 0; --i) {
+          if (m.W[i] < 100.f) {
+            for (int j = 0; j < 6; ++j) m.V2[i * 6 + j] = 0.f;
+            deg = 1;
+          } else {
+            break;
+          }
         }
+        st->degenerate = deg;
       }
-      st->degenerate = deg;
-      inv6_lu(V, Vi);
-      for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-          double s = 0;
-          for (int k = 0; k < 6; ++k) s += (double)Vi[i * 6 + k] * (double)V2[k * 6 + j];
-          st->matP[i * 6 + j] = (float)s;
-        }
-    }
-    if (st->degenerate) {  // :1810-1815
-      float X2[6];
-      for (int i = 0; i < 6; ++i) X2[i] = X[i];
-      for (int i = 0; i < 6; ++i) {
-        double s = 0;
-        for (int k = 0; k < 6; ++k) s += (double)st->matP[i * 6 + k] * (double)X2[k];
-        X[i] = (float)s;
+      __syncwarp();
+      warp_inv6_lu(m, lane);
+      for (int e = lane; e < 36; e += 32) {  // matP = matV.inv() * matV2 (f64 accumulation, cv::gemm)
+        const int i = e / 6, j = e % 6;
+        double acc = 0;
+        for (int k = 0; k < 6; ++k) acc += (double)m.Vi[i * 6 + k] * (double)m.V2[k * 6 + j];
+        st->matP[e] = (float)acc;
       }
+      __threadfence_block();
+      __syncwarp();
     }
-    for (int i = 0; i < 6; ++i) st->pose[i] += X[i];
+    float xi = lane < 6 ? m.X[lane] : 0.f;
+    if (st->degenerate && lane < 6) {  // :1810-1815
+      double acc = 0;
+      for (int k = 0; k < 6; ++k) acc += (double)st->matP[lane * 6 + k] * (double)m.X[k];
+      xi = (float)acc;
+    }
+    if (lane < 6) st->pose[lane] += xi;
     const float r2d = 57.29578f;  // pcl::rad2deg(float)
-    const float rx = X[0] * r2d, ry = X[1] * r2d, rz = X[2] * r2d;
+    const float x0 = __shfl_sync(FULL, xi, 0), x1 = __shfl_sync(FULL, xi, 1), x2 = __shfl_sync(FULL, xi, 2);
+    const float x3 = __shfl_sync(FULL, xi, 3), x4 = __shfl_sync(FULL, xi, 4), x5 = __shfl_sync(FULL, xi, 5);
+    const float rx = x0 * r2d, ry = x1 * r2d, rz = x2 * r2d;
     const float dr = (float)sqrt((double)rx * rx + (double)ry * ry + (double)rz * rz);
-    const float tx = X[3] * 100, ty = X[4] * 100, tz = X[5] * 100;
+    const float tx = x3 * 100, ty = x4 * 100, tz = x5 * 100;
     const float dt = (float)sqrt((double)tx * tx + (double)ty * ty + (double)tz * tz);
-    st->delta_r = dr;
-    st->delta_t = dt;
+    if (lane == 0) { st->delta_r = dr; st->delta_t = dt; }
     conv = ((double)dr < 0.05) && ((double)dt < 0.05);
   }
-  for (int i = 0; i < 6; ++i) st->pose_hist[it][i] = st->pose[i];
-  st->iter = it + 1;
+  __syncwarp();
+  if (lane < 6) st->pose_hist[it][lane] = st->pose[lane];
+  int iter = it + 1;
   if (nsel < 50) {
     // Nothing changed, so every remaining iteration of the reference's loop would redo identical work
     // and bail out at :1722 again (quirk q2): record them and stop instead of burning launches.
     for (int k = it + 1; k < st->max_iter; ++k) {
-      for (int i = 0; i < 6; ++i) st->pose_hist[k][i] = st->pose[i];
-      st->nsel_hist[k] = nsel;
+      if (lane < 6) st->pose_hist[k][lane] = st->pose[lane];
+      if (lane == 0) st->nsel_hist[k] = nsel;
     }
-    st->iter = st->max_iter;
+    iter = st->max_iter;
   }
-  if (conv) { st->converged = 1; st->done = 1; }
-  if (st->iter >= st->max_iter) st->done = 1;
+  const bool done = conv || iter >= st->max_iter;
+  __syncwarp();
+  if (!done) warp_refresh_transform(st, lane);
+  if (lane == 0) {
+    st->iter = iter;
+    if (conv) st->converged = 1;
+    if (done) st->done = 1;
+  }
 }
 
-// mode 0: LM iteration on the device state.  mode 1: one surfOptimization pass with per-point outputs
-// (no state update); T_override (12 floats) replaces the pose-derived transform when non-null.
-__global__ void __launch_bounds__(S2M_THREADS)
-s2m_iter_kernel(const float4* __restrict__ scan, int nq, const float4* __restrict__ map4,
-                const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start, const GridParams g,
-                LmDevState* __restrict__ st, double* __restrict__ partials, unsigned* __restrict__ ticket,
-                const float* __restrict__ T_override, SurfDebugOut dbg, int mode) {
+// ------------------------------------------------------------------------------------------------
+// Per-iteration launches (mode 0: LM iteration on the device state; mode 1: one surfOptimization pass
+// with per-point outputs and no state update, T_override replacing the pose-derived transform):
+//
+//   s2m_main_kernel  one thread per scan point: transform, phase-1 search (small gate), plane fit, Jacobian
+//                    row, FP64 block reduction -> partials[block].  A point whose 5 neighbours are not all
+//                    inside the phase-1 radius is NOT searched further here: its index goes to the block's
+//                    segment of `fail_seg` (deterministic order) so no warp ever waits for a straggler.
+//                    The last block to finish turns the per-block counts into one dense list.
+//   s2m_left_kernel  the leftover points (about 2 % on a dense map, all of them on a sparse one), 32 per
+//                    warp: warp-cooperative full-gate search per point, then the plane fit lane-parallel.
+//                    Its blocks also fold the main kernel's partials; the last block adds everything in a
+//                    fixed order and runs the 6x6 tail of LMOptimization (lm_finalize_warp).
+struct S2mArgs {
+  const float4* scan;
+  int nq;
+  const float4* map4;
+  const float4* map_sorted;
+  const uint32_t* cell_start;
+  GridParams g;
+  LmDevState* st;
+  double* partials_main;   // [main blocks][S2M_SUMS]
+  double* partials_left;   // [left blocks][S2M_SUMS]
+  int* block_nfail;        // [main blocks]
+  int* fail_seg;           // [main blocks][S2M_THREADS]
+  int* fail_off;           // [main blocks + 1] exclusive scan of block_nfail
+  int* fail_total;         // [1]
+  unsigned* ticket;        // [2]: main, left
+  const float* T_override;
+  SurfDebugOut dbg;
+  int mode;
+  int main_blocks;
+};
+
+struct RowAcc {  // which product of the staged row a reducing thread owns
+  int a, b;
+  bool live;
+};
+__device__ __forceinline__ RowAcc row_acc_of(const int p) {
+  RowAcc r;
+  r.live = p <= 27;
+  if (p < 21) {  // upper-triangle pair index -> (a, b)
+    int q = p, a = 0;
+    while (q >= 6 - a) { q -= 6 - a; ++a; }
+    r.a = a; r.b = a + q;
+  } else if (p < 27) {
+    r.a = p - 21; r.b = 6;
+  } else {
+    r.a = 7; r.b = 7;  // p == 27: accepted count (flag * flag)
+  }
+  return r;
+}
+
+// plane fit + Jacobian row of one point whose neighbours are known; writes the debug outputs in mode 1
+__device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, const float4 ori, const float4 sel,
+                                             const Top5& t, const LmTrig& trig, float row[6], float& rhs, bool& flag,
+                                             bool& tie) {
+  float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641 (the gate is the reference's 1.0)
+  flag = false; tie = false;
+  if (found) {
+    float4 nbr[5];
+    nbr[0] = __ldg(A.map4 + t.i(t.k0)); nbr[1] = __ldg(A.map4 + t.i(t.k1)); nbr[2] = __ldg(A.map4 + t.i(t.k2));
+    nbr[3] = __ldg(A.map4 + t.i(t.k3)); nbr[4] = __ldg(A.map4 + t.i(t.k4));
+    flag = plane_residual(ori, sel, nbr, coeff);
+    tie = t.tie();
+    if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (flag) jacobian_row(trig, ori, coeff, row, rhs);
+  if (A.mode == 1) {
+    if (A.dbg.nn_idx) {
+      int* o = A.dbg.nn_idx + (size_t)i * 5;
+      o[0] = found ? t.i(t.k0) : -1; o[1] = found ? t.i(t.k1) : -1; o[2] = found ? t.i(t.k2) : -1;
+      o[3] = found ? t.i(t.k3) : -1; o[4] = found ? t.i(t.k4) : -1;
+    }
+    if (A.dbg.nn_d2) {
+      float* o = A.dbg.nn_d2 + (size_t)i * 5;
+      o[0] = t.d(t.k0); o[1] = t.d(t.k1); o[2] = t.d(t.k2); o[3] = t.d(t.k3); o[4] = t.d(t.k4);
+    }
+    if (A.dbg.coeff) A.dbg.coeff[i] = coeff;
+    if (A.dbg.flag) A.dbg.flag[i] = flag ? 1 : 0;
+    if (A.dbg.tie) A.dbg.tie[i] = tie ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
+s2m_main_kernel(const S2mArgs A) {
   __shared__ float sT[12];
   __shared__ LmTrig sTrig;
-  __shared__ float rows[S2M_THREADS][8];   // 6 Jacobian entries, rhs, accepted flag
+  __shared__ float rows[S2M_THREADS][8];  // 6 Jacobian entries, rhs, accepted flag
   __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
-  __shared__ int s_ties;
+  __shared__ int s_ties, s_wfail[S2M_THREADS / 32];
   __shared__ bool s_last;
 
-  if (mode == 0 && st->done) return;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    if (T_override) {
-      for (int k = 0; k < 12; ++k) sT[k] = T_override[k];
-    } else {
-      pose_to_T(st->pose, sT);  // updatePointAssociateToMap (:1613-1616)
-    }
-    sTrig = lm_trig(st->pose);
+  if (A.mode == 0 && A.st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
+  if (tid == 32) {
+    sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
+    sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
     s_ties = 0;
   }
   __syncthreads();
@@ -221,104 +653,218 @@ s2m_iter_kernel(const float4* __restrict__ scan, int nq, const float4* __restric
   const int i = blockIdx.x * S2M_THREADS + tid;
   float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float rhs = 0.f;
-  bool flag = false, tie = false;
-  if (i < nq) {
-    const float4 ori = scan[i];
+  bool flag = false, tie = false, need2 = false;
+  if (i < A.nq) {
+    const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
     Top5 t;
-    grid_knn5(sel, g, map_sorted, cell_start, t);
-    float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t.d4 < g.gate_d2) {  // :1641 (the gate is the reference's 1.0)
-      float4 nbr[5];
-      nbr[0] = __ldg(map4 + t.i0); nbr[1] = __ldg(map4 + t.i1); nbr[2] = __ldg(map4 + t.i2);
-      nbr[3] = __ldg(map4 + t.i3); nbr[4] = __ldg(map4 + t.i4);
-      flag = plane_residual(ori, sel, nbr, coeff);
-      tie = (t.d0 == t.d1) || (t.d1 == t.d2) || (t.d2 == t.d3) || (t.d3 == t.d4) || (t.d4 == t.rej);
-      if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A.g.gate1_d2 < A.g.gate_d2) {
+      grid_knn5(sel, A.g, A.g.gate1_d2, A.map_sorted, A.cell_start, t);
+      need2 = !(t.d(t.k4) < A.g.gate1_d2);
+    } else {
+      need2 = true;
     }
-    if (flag) jacobian_row(sTrig, ori, coeff, row, rhs);
-    if (mode == 1) {
-      if (dbg.nn_idx) {
-        int* o = dbg.nn_idx + (size_t)i * 5;
-        o[0] = t.i0; o[1] = t.i1; o[2] = t.i2; o[3] = t.i3; o[4] = t.i4;
-      }
-      if (dbg.nn_d2) {
-        float* o = dbg.nn_d2 + (size_t)i * 5;
-        o[0] = t.d0; o[1] = t.d1; o[2] = t.d2; o[3] = t.d3; o[4] = t.d4;
-      }
-      if (dbg.coeff) dbg.coeff[i] = coeff;
-      if (dbg.flag) dbg.flag[i] = flag ? 1 : 0;
-      if (dbg.tie) dbg.tie[i] = tie ? 1 : 0;
-    }
+    if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
   }
-  if (mode == 1) return;
-
+  // leftover indices, in thread order, into this block's segment
+  const unsigned fm = __ballot_sync(0xffffffffu, need2);
+  if (lane == 0) s_wfail[warp] = __popc(fm);
 #pragma unroll
   for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
   rows[tid][6] = rhs;
   rows[tid][7] = flag ? 1.f : 0.f;
   if (flag && tie) atomicAdd(&s_ties, 1);
   __syncthreads();
-
+  if (need2) {
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wfail[w];
+    A.fail_seg[(size_t)blockIdx.x * S2M_THREADS + base + __popc(fm & ((1u << lane) - 1u))] = i;
+  }
   // 27 FP64 sums + count: thread (slice, p) adds its 32 rows' product p; products of two floats are
   // exact in double, so only the order of additions differs from cv::gemm's.
   {
-    const int p = tid & 31, slice = tid >> 5;
-    int a = 0, b = 0;
-    if (p < 21) {  // upper-triangle pair index -> (a, b)
-      int q = p;
-      a = 0;
-      while (q >= 6 - a) { q -= 6 - a; ++a; }
-      b = a + q;
-    } else if (p < 27) {
-      a = p - 21; b = 6;
-    } else {
-      a = 7; b = 7;  // p == 27: accepted count (flag*flag); p > 27 unused (adds zeros below)
-    }
+    const int p = lane, slice = warp;
+    const RowAcc ra = row_acc_of(p);
     double acc = 0.0;
-    if (p <= 27) {
+    if (ra.live) {
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const float* rr = rows[slice * 32 + r];
-        acc += (double)rr[a] * (double)rr[b];
+        acc += (double)rr[ra.a] * (double)rr[ra.b];
       }
     }
     red[slice][p] = acc;
   }
   __syncthreads();
   if (tid < S2M_SUMS) {
-    double s = 0.0;
+    double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k < S2M_THREADS / 32; ++k) s += red[k][tid];
-    if (tid == 28) s = (double)s_ties;
-    partials[(size_t)blockIdx.x * S2M_SUMS + tid] = s;
+    for (int k = 0; k < S2M_THREADS / 32; ++k) sum += red[k][tid];
+    if (tid == 28) sum = (double)s_ties;
+    A.partials_main[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
+  }
+  if (tid == 0) {
+    int nf = 0;
+    for (int w = 0; w < S2M_THREADS / 32; ++w) nf += s_wfail[w];
+    A.block_nfail[blockIdx.x] = nf;
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) {
-    const unsigned prev = atomicAdd(ticket, 1u);
-    s_last = (prev == gridDim.x - 1);
+  if (tid == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block: exclusive scan of the per-block leftover counts -> fail_off (block order) ----
+  __threadfence();
+  __shared__ int s_wsum[S2M_THREADS / 32];
+  __shared__ int s_carry;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < (int)gridDim.x; b0 += S2M_THREADS) {
+    const int b = b0 + tid;
+    const int cnt = b < (int)gridDim.x ? __ldcg(A.block_nfail + b) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int base = s_carry;
+    for (int w = 0; w < warp; ++w) base += s_wsum[w];
+    if (b < (int)gridDim.x) A.fail_off[b] = base + incl - cnt;
+    __syncthreads();
+    if (tid == S2M_THREADS - 1) s_carry = base + incl;
+    __syncthreads();
   }
+  if (tid == 0) {
+    A.fail_off[gridDim.x] = s_carry;
+    *A.fail_total = s_carry;
+    *A.ticket = 0u;
+  }
+}
+
+constexpr int LEFT_THREADS = 256;
+__global__ void __launch_bounds__(LEFT_THREADS, 2)
+s2m_left_kernel(const S2mArgs A) {
+  __shared__ float sT[12];
+  __shared__ LmTrig sTrig;
+  __shared__ float rows[LEFT_THREADS][8];
+  __shared__ double red[LEFT_THREADS / 32][S2M_SUMS];
+  __shared__ int s_ties;
+  __shared__ bool s_last;
+  __shared__ FinSmem s_fin;
+
+  if (A.mode == 0 && A.st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];
+  if (tid == 32) {
+    sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
+    sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
+    s_ties = 0;
+  }
+  __syncthreads();
+  const bool all_points = !(A.g.gate1_d2 < A.g.gate_d2);  // single-phase: the main kernel did not run
+  const int total = all_points ? A.nq : *A.fail_total;
+  const int warps_per_grid = gridDim.x * (LEFT_THREADS / 32);
+  // points per warp: as few as possible (each point is a serial chain of dependent look-ups, so spreading
+  // them over all resident warps hides that latency), up to 32 when there are more points than warps
+  const int per_warp = min(32, max(1, (total + warps_per_grid - 1) / warps_per_grid));
+  const int nbatch = (total + per_warp - 1) / per_warp;
+  const RowAcc ra = row_acc_of(lane);
+  double acc = 0.0;  // this thread's share of the block's sums, kept across rounds
+  int ties = 0;
+  // rounds: in round r, warp w of the grid owns batch r * warps_per_grid + (block, warp) — a static map,
+  // so the order of every addition is fixed.
+  for (int r0 = 0; r0 < nbatch; r0 += warps_per_grid) {
+    const int batch = r0 + blockIdx.x * (LEFT_THREADS / 32) + warp;
+    float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float rhs = 0.f;
+    bool flag = false, tie = false;
+    if (batch < nbatch) {
+      const int e0 = batch * per_warp;
+      const int cnt = min(per_warp, total - e0);
+      int mine = -1;
+      if (lane < cnt) {
+        const int e = e0 + lane;
+        if (all_points) {
+          mine = e;
+        } else {  // leftover e lives in the segment of the main block whose offset range contains it
+          int lo = 0, hi = A.main_blocks;  // invariant: fail_off[lo] <= e < fail_off[hi]
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(A.fail_off + mid) <= e) lo = mid; else hi = mid;
+          }
+          mine = A.fail_seg[(size_t)lo * S2M_THREADS + (e - __ldg(A.fail_off + lo))];
+        }
+      }
+      float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
+      if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
+      Top5 t;
+      t.init(A.g.gate_d2);
+      for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
+        float4 q;
+        q.x = __shfl_sync(0xffffffffu, sel.x, j); q.y = __shfl_sync(0xffffffffu, sel.y, j);
+        q.z = __shfl_sync(0xffffffffu, sel.z, j); q.w = 0.f;
+        Top5 tj;
+        warp_knn5(q, A.g, A.map_sorted, A.cell_start, lane, tj);
+        if (lane == j) t = tj;
+      }
+      if (mine >= 0) finish_point(A, mine, ori, sel, t, sTrig, row, rhs, flag, tie);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
+    rows[tid][6] = rhs;
+    rows[tid][7] = flag ? 1.f : 0.f;
+    if (flag && tie) ++ties;
+    __syncthreads();
+    if (ra.live) {  // every warp owns the slice of rows its own lanes staged
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float* rr = rows[warp * 32 + r];
+        acc += (double)rr[ra.a] * (double)rr[ra.b];
+      }
+    }
+    __syncthreads();
+  }
+  // fold this block's share of the main kernel's partial rows (same (slice, p) ownership)
+#pragma unroll 4
+  for (int b = blockIdx.x * (LEFT_THREADS / 32) + warp; !all_points && b < A.main_blocks; b += warps_per_grid)
+    acc += __ldcg(A.partials_main + (size_t)b * S2M_SUMS + lane);
+  if (ties) atomicAdd(&s_ties, ties);
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (tid < S2M_SUMS) {
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < LEFT_THREADS / 32; ++k) sum += red[k][tid];
+    if (tid == 28) sum += (double)s_ties;  // main kernel's tie counts arrive through slot 28 of its partials
+    A.partials_left[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
+  }
+  if (A.mode == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(A.ticket + 1, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  {  // fixed-order sum over blocks: 8 slices of blocks, then the slices
-    const int p = tid & 31, slice = tid >> 5;
-    double acc = 0.0;
-    for (unsigned b = slice; b < gridDim.x; b += S2M_THREADS / 32) acc += __ldcg(partials + (size_t)b * S2M_SUMS + p);
-    red[slice][p] = acc;
+  {  // fixed-order sum over the left blocks: 8 slices of blocks, then the slices
+    double a2 = 0.0;
+#pragma unroll 8
+    for (unsigned b = warp; b < gridDim.x; b += LEFT_THREADS / 32) a2 += __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
+    red[warp][lane] = a2;
   }
   __syncthreads();
   if (tid < S2M_SUMS) {
-    double s = 0.0;
+    double sum = 0.0;
 #pragma unroll
-    for (int k = 0; k < S2M_THREADS / 32; ++k) s += red[k][tid];
-    red[0][tid] = s;
+    for (int k = 0; k < LEFT_THREADS / 32; ++k) sum += red[k][tid];
+    red[0][tid] = sum;
   }
   __syncthreads();
-  if (tid == 0) {
-    lm_finalize(st, red[0]);
-    *ticket = 0u;
+  if (tid < 32) {
+    lm_finalize_warp(A.st, red[0], s_fin, tid);
+    if (tid == 0) A.ticket[1] = 0u;
   }
 }
 
@@ -327,40 +873,78 @@ static int check_grid(Ctx* c) {
   return LIOGPU_OK;
 }
 
+// device scratch shared by both entry points
+static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& main_blocks, int& left_blocks) {
+  main_blocks = div_up(n, S2M_THREADS);
+  left_blocks = c->sm_count * 2;  // two resident CTAs per SM; rounds cover anything beyond one batch per warp
+  LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
+  LIOGPU_CUDA_OK(c, c->partials.reserve(((size_t)main_blocks + left_blocks) * S2M_SUMS * sizeof(double)));
+  LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)main_blocks * S2M_THREADS + 2 * (size_t)main_blocks + 64) * sizeof(int)));
+  if (!c->block_counter.p) {
+    LIOGPU_CUDA_OK(c, c->block_counter.reserve(64));
+    LIOGPU_CUDA_OK(c, cudaMemsetAsync(c->block_counter.p, 0, 64, c->stream));
+  }
+  A.scan = scan4; A.nq = n;
+  A.map4 = c->map4.as<float4>(); A.map_sorted = c->map_sorted.as<float4>(); A.cell_start = c->cell_start.as<uint32_t>();
+  A.g = c->grid;
+  A.st = c->lm_state.as<LmDevState>();
+  A.partials_main = c->partials.as<double>();
+  A.partials_left = A.partials_main + (size_t)main_blocks * S2M_SUMS;
+  int* fb = c->fail_buf.as<int>();
+  A.fail_seg = fb;
+  A.fail_off = fb + (size_t)main_blocks * S2M_THREADS;
+  A.block_nfail = A.fail_off + main_blocks + 1;
+  A.fail_total = A.block_nfail + main_blocks;
+  A.ticket = c->block_counter.as<unsigned>();
+  A.T_override = nullptr;
+  A.dbg = SurfDebugOut{nullptr, nullptr, nullptr, nullptr, nullptr};
+  A.mode = 0;
+  A.main_blocks = main_blocks;
+  return LIOGPU_OK;
+}
+
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info) {
   int rc = check_grid(c);
   if (rc != LIOGPU_OK) return rc;
   if (max_iter < 1 || max_iter > LIOGPU_MAX_ITER) { c->err = "max_iter out of range"; return LIOGPU_E_INVALID; }
-  const int blocks = div_up(n, S2M_THREADS);
-  LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
-  LIOGPU_CUDA_OK(c, c->partials.reserve((size_t)blocks * S2M_SUMS * sizeof(double)));
-  if (!c->block_counter.p) {
-    LIOGPU_CUDA_OK(c, c->block_counter.reserve(64));
-    LIOGPU_CUDA_OK(c, cudaMemsetAsync(c->block_counter.p, 0, 64, c->stream));
-  }
+  S2mArgs A;
+  int main_blocks = 0, left_blocks = 0;
+  rc = prepare_args(c, scan4, n, A, main_blocks, left_blocks);
+  if (rc != LIOGPU_OK) return rc;
   LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
   memset(h, 0, sizeof(LmDevState));
   for (int k = 0; k < 6; ++k) h->pose[k] = pose_io[k];
   for (int k = 0; k < 36; ++k) h->matP[k] = matP_io[k];
   h->degenerate = *degenerate_io;
   h->max_iter = max_iter;
-  LmDevState* d = c->lm_state.as<LmDevState>();
+  LmDevState* d = A.st;
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  SurfDebugOut dbg{nullptr, nullptr, nullptr, nullptr, nullptr};
-  for (int it = 0; it < max_iter; ++it) {
-    s2m_iter_kernel<<<blocks, S2M_THREADS, 0, c->stream>>>(scan4, n, c->map4.as<float4>(), c->map_sorted.as<float4>(),
-                                                           c->cell_start.as<uint32_t>(), c->grid, d,
-                                                           c->partials.as<double>(), c->block_counter.as<unsigned>(),
-                                                           nullptr, dbg, 0);
+  lm_prepare_kernel<<<1, 32, 0, c->stream>>>(d);
+  c->launches++;
+  // The loop never waits for the host inside a chunk: S2M_CHUNK iterations are enqueued back to back
+  // (a launch that finds `done` set exits at once), then the state block is read back — the same single
+  // read-back a converged registration needs anyway.  Only scans that need more than S2M_CHUNK iterations
+  // pay a second round trip.
+  const int S2M_CHUNK = 6;
+  int launched = 0;
+  for (;;) {
+    const int todo = (max_iter - launched) < S2M_CHUNK ? (max_iter - launched) : S2M_CHUNK;
+    const bool two_phase = A.g.gate1_d2 < A.g.gate_d2;
+    for (int it = 0; it < todo; ++it) {
+      if (two_phase) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+      s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
+    }
+    launched += todo;
+    c->launches += (two_phase ? 2 : 1) * todo;
+    LIOGPU_CUDA_OK(c, cudaGetLastError());
+    LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(LmDevState), cudaMemcpyDeviceToHost, c->stream));
+    LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    LIOGPU_CUDA_OK(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (h->done || launched >= max_iter) break;
   }
-  c->launches += max_iter;
-  LIOGPU_CUDA_OK(c, cudaGetLastError());
-  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(LmDevState), cudaMemcpyDeviceToHost, c->stream));
-  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  LIOGPU_CUDA_OK(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   for (int k = 0; k < 6; ++k) pose_io[k] = h->pose[k];
   for (int k = 0; k < 36; ++k) matP_io[k] = h->matP[k];
   *degenerate_io = h->degenerate;
@@ -388,39 +972,40 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
   if (rc != LIOGPU_OK) return rc;
   if ((pose6 == nullptr) == (T12 == nullptr)) { c->err = "exactly one of pose6 / T12 must be given"; return LIOGPU_E_INVALID; }
   if (n <= 0) return LIOGPU_OK;
-  LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
-  LIOGPU_CUDA_OK(c, c->partials.reserve((size_t)div_up(n, S2M_THREADS) * S2M_SUMS * sizeof(double)));
+  S2mArgs A;
+  int main_blocks = 0, left_blocks = 0;
+  rc = prepare_args(c, scan4, n, A, main_blocks, left_blocks);
+  if (rc != LIOGPU_OK) return rc;
   LIOGPU_CUDA_OK(c, c->misc.reserve(256));
   LIOGPU_CUDA_OK(c, c->dbg_idx.reserve((size_t)n * 5 * sizeof(int)));
   LIOGPU_CUDA_OK(c, c->dbg_d2.reserve((size_t)n * 5 * sizeof(float)));
   LIOGPU_CUDA_OK(c, c->dbg_coeff.reserve((size_t)n * sizeof(float4)));
   LIOGPU_CUDA_OK(c, c->dbg_flag.reserve((size_t)n));
   LIOGPU_CUDA_OK(c, c->dbg_tie.reserve((size_t)n));
-  if (!c->block_counter.p) {
-    LIOGPU_CUDA_OK(c, c->block_counter.reserve(64));
-    LIOGPU_CUDA_OK(c, cudaMemsetAsync(c->block_counter.p, 0, 64, c->stream));
-  }
   LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
   memset(h, 0, sizeof(LmDevState));
   if (pose6) for (int k = 0; k < 6; ++k) h->pose[k] = pose6[k];
-  LmDevState* d = c->lm_state.as<LmDevState>();
+  LmDevState* d = A.st;
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
-  float* d_T = nullptr;
+  lm_prepare_kernel<<<1, 32, 0, c->stream>>>(d);
+  c->launches++;
   if (T12) {
-    d_T = c->misc.as<float>() + 16;
+    float* d_T = c->misc.as<float>() + 16;
     float* hT = reinterpret_cast<float*>((char*)c->h_pinned + 3072);
     for (int k = 0; k < 12; ++k) hT[k] = T12[k];
     LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d_T, hT, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    A.T_override = d_T;
   }
-  SurfDebugOut dbg{c->dbg_idx.as<int>(), c->dbg_d2.as<float>(), c->dbg_coeff.as<float4>(),
-                   c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
+  A.dbg = SurfDebugOut{c->dbg_idx.as<int>(), c->dbg_d2.as<float>(), c->dbg_coeff.as<float4>(),
+                       c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
+  A.mode = 1;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  s2m_iter_kernel<<<div_up(n, S2M_THREADS), S2M_THREADS, 0, c->stream>>>(
-      scan4, n, c->map4.as<float4>(), c->map_sorted.as<float4>(), c->cell_start.as<uint32_t>(), c->grid, d,
-      c->partials.as<double>(), c->block_counter.as<unsigned>(), d_T, dbg, 1);
-  c->launches++;
+  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+  s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
+  c->launches += 2;
   LIOGPU_CUDA_OK(c, cudaGetLastError());
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  const SurfDebugOut& dbg = A.dbg;
   if (nn_idx) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(nn_idx, dbg.nn_idx, (size_t)n * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (nn_d2) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(nn_d2, dbg.nn_d2, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   if (coeff) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(coeff, dbg.coeff, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));

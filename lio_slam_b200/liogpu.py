@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libliogpu.so")
+LIB_PATH = os.environ.get("LIOGPU_LIB") or os.path.join(_HERE, "libliogpu.so")  # LIOGPU_LIB: A/B builds
 
 LIOGPU_MAX_ITER = 30
 OK = 0
@@ -29,7 +29,7 @@ class Params(C.Structure):
                 ("downsample_rate", C.c_int), ("point_filter_num", C.c_int),
                 ("lidar_min_front", C.c_float), ("lidar_min_back", C.c_float), ("lidar_min_left", C.c_float),
                 ("lidar_min_right", C.c_float), ("lidar_max_range", C.c_float), ("lidar_max_intensity", C.c_float),
-                ("knn_cell_size", C.c_float), ("reserved", C.c_int * 7)]
+                ("knn_cell_size", C.c_float), ("knn_phase1_radius", C.c_float), ("reserved", C.c_int * 6)]
 
 
 class S2MInfo(C.Structure):

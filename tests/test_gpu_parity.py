@@ -126,10 +126,11 @@ def test_knn_ties_are_logged_and_canonical(gpu, oracle):
     assert_biteq(got["nn_d2"], ref["nn_d2"])
 
 
-@pytest.mark.parametrize("cell", [0.25, 0.5, 1.0, 2.0])
-def test_knn_independent_of_cell_size(oracle, small_case, cell):
+@pytest.mark.parametrize("cell,r1", [(0.25, 0.0), (0.5, -1.0), (1.0, 0.3), (2.0, 0.6), (0.0, 0.45), (0.3, 0.79)])
+def test_knn_independent_of_cell_size(oracle, small_case, cell, r1):
+    # cell edge and phase-1 radius are tuning knobs: results must not depend on them
     from lio_slam_b200.liogpu import LioGpu
-    g = LioGpu(knn_cell_size=cell)
+    g = LioGpu(knn_cell_size=cell, knn_phase1_radius=r1)
     try:
         ds, _ = oracle.voxel_grid(small_case["scan4"], 0.8)
         T = oracle.pose_to_T(small_case["guess"])
@@ -138,7 +139,10 @@ def test_knn_independent_of_cell_size(oracle, small_case, cell):
         got = g.surf_optimization(ds, T12=T)
         gate = ref["nn_d2"][:, 4] < 1.0
         assert np.array_equal(got["nn_idx"][gate], ref["nn_idx"][gate])
+        assert_biteq(got["nn_d2"][gate], ref["nn_d2"][gate])
+        assert np.array_equal(got["tie"][gate], ref["tie"][gate])
         assert np.array_equal(got["flag"], ref["flag"])
+        assert_biteq(got["coeff"], ref["coeff"])
     finally:
         g.close()
 
