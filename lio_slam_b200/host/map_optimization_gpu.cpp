@@ -1,0 +1,179 @@
+// map_optimization_gpu.cpp — bodies of the mirrored member functions: thin calls into the C ABI.
+#include "map_optimization_gpu.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+namespace liorf_gpu {
+
+int ImageProjection::projectPointCloud() {
+  fullCloud.resize(laserCloudIn.size());
+  int n_out = 0;
+  const int enabled = (deskewFlag != -1 && imuAvailable) ? 1 : 0;  // imageProjection.cpp:547
+  const int st = liogpu_deskew(ctx_, laserCloudIn.data(), (int)laserCloudIn.size(), sizeof(PointXYZIRT), timeScanCur,
+                               imuTime.data(), imuRotX.data(), imuRotY.data(), imuRotZ.data(), imuPointerCur + 1, enabled,
+                               fullCloud.data(), sizeof(PointType), (int)fullCloud.size(), &n_out);
+  fullCloud.resize(st < 0 ? 0 : n_out);
+  return st;
+}
+
+mapOptimization::mapOptimization(const liogpu_params& params) : params_(params) {
+  const int st = liogpu_create(&ctx_, &params_);  // allocateMemory (mapOptmization.cpp:316-349)
+  if (st != LIOGPU_OK) throw std::runtime_error("liogpu_create failed (no sm_100 GPU? there is no CPU fallback)");
+}
+mapOptimization::~mapOptimization() { liogpu_destroy(ctx_); }
+const char* mapOptimization::lastError() const { return liogpu_last_error(ctx_); }
+
+static inline float pointDistance(const PointType& a, const PointType& b) {  // common_lib.cpp:33-37
+  return std::sqrt((a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z));
+}
+
+void mapOptimization::extractSurroundingKeyFrames() {
+  if (cloudKeyPoses3D.empty()) return;  // :1592
+  extractNearby();
+}
+
+// Host logic, as in the reference: which keyframes form the local map.  The key-pose VoxelGrid (leaf
+// surroundingKeyframeDensity, :1535-1541) keeps one pose per occupied voxel; with a few hundred poses this
+// stays on the host.  (:1542 replaces each centroid by its nearest key pose, so the result is a subset of
+// the key poses: the first pose seen in each voxel is taken here.)
+void mapOptimization::extractNearby() {
+  const PointType& last = cloudKeyPoses3D.back();
+  std::vector<int> near;
+  for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i)
+    if (pointDistance(cloudKeyPoses3D[i], last) <= surroundingKeyframeSearchRadius) near.push_back(i);
+  std::vector<int> ids;
+  const float inv = 1.0f / surroundingKeyframeDensity;
+  std::vector<long long> seen;
+  for (int i : near) {
+    const PointType& p = cloudKeyPoses3D[i];
+    const long long key = ((long long)std::floor(p.x * inv) * 73856093LL) ^ ((long long)std::floor(p.y * inv) * 19349663LL) ^
+                          ((long long)std::floor(p.z * inv) * 83492791LL);
+    if (std::find(seen.begin(), seen.end(), key) == seen.end()) { seen.push_back(key); ids.push_back(i); }
+  }
+  for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {  // :1545-1551 keyframes younger than 10 s
+    if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) {
+      if (std::find(ids.begin(), ids.end(), i) == ids.end()) ids.push_back(i);
+    } else {
+      break;
+    }
+  }
+  surroundingKeyPosesDS = ids;
+  extractCloud(ids);
+}
+
+void mapOptimization::extractCloud(const std::vector<int>& ids) {
+  std::vector<int> use;
+  std::vector<float> poses;
+  for (int id : ids) {
+    if (pointDistance(cloudKeyPoses3D[id], cloudKeyPoses3D.back()) > surroundingKeyframeSearchRadius) continue;  // :1562
+    use.push_back(id);
+    const PointTypePose& p = cloudKeyPoses6D[id];
+    const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+    poses.insert(poses.end(), pose6, pose6 + 6);
+  }
+  // quirk q1: the reference rebuilds the KD-tree every scan; the device index is rebuilt only when the
+  // keyframe set or a pose in it changed
+  if (use == mapKeyIds_ && poses == mapKeyPoses_) return;
+  int n_map = 0;
+  if (fetchLocalMap) {
+    laserCloudSurfFromMapDS.resize(1);
+    int st = liogpu_build_local_map(ctx_, use.data(), poses.data(), (int)use.size(), params_.surrounding_keyframe_map_leaf_size,
+                                    &n_map, laserCloudSurfFromMapDS.data(), sizeof(PointType), 0);
+    if (st == LIOGPU_E_CAPACITY) {
+      laserCloudSurfFromMapDS.resize(n_map);
+      st = liogpu_build_local_map(ctx_, use.data(), poses.data(), (int)use.size(), params_.surrounding_keyframe_map_leaf_size,
+                                  &n_map, laserCloudSurfFromMapDS.data(), sizeof(PointType), n_map);
+    }
+    lastStatus = st;
+    laserCloudSurfFromMapDS.resize(st < 0 ? 0 : n_map);
+  } else {
+    lastStatus = liogpu_build_local_map(ctx_, use.data(), poses.data(), (int)use.size(),
+                                        params_.surrounding_keyframe_map_leaf_size, &n_map, nullptr, 0, 0);
+  }
+  laserCloudSurfFromMapDSNum = n_map;
+  mapKeyIds_ = use;
+  mapKeyPoses_ = poses;
+}
+
+void mapOptimization::downsampleCurrentScan() {
+  laserCloudSurfLastDS.resize(laserCloudSurfLast.size());
+  int n = 0;
+  lastStatus = liogpu_voxel_downsample(ctx_, laserCloudSurfLast.data(), (int)laserCloudSurfLast.size(), sizeof(PointType),
+                                       params_.mapping_surf_leaf_size, laserCloudSurfLastDS.data(), sizeof(PointType),
+                                       (int)laserCloudSurfLastDS.size(), &n);
+  laserCloudSurfLastDS.resize(lastStatus < 0 ? 0 : n);
+  laserCloudSurfLastDSNum = (int)laserCloudSurfLastDS.size();
+}
+
+void mapOptimization::scan2MapOptimization() {
+  if (cloudKeyPoses3D.empty()) return;  // :1841
+  int deg = isDegenerate ? 1 : 0;
+  lastStatus = liogpu_scan2map(ctx_, laserCloudSurfLastDS.data(), laserCloudSurfLastDSNum, sizeof(PointType), transformTobeMapped,
+                               matP, &deg, LIOGPU_MAX_ITER, &lastInfo);
+  isDegenerate = deg != 0;
+  // transformUpdate() (:1861, IMU roll/pitch slerp + clamps) stays with the caller, as in the reference
+}
+
+void mapOptimization::downsampleAndScan2Map() {
+  if (cloudKeyPoses3D.empty()) { downsampleCurrentScan(); return; }
+  int deg = isDegenerate ? 1 : 0, n_ds = 0;
+  laserCloudSurfLastDS.resize(laserCloudSurfLast.size());
+  lastStatus = liogpu_downsample_scan2map(ctx_, laserCloudSurfLast.data(), (int)laserCloudSurfLast.size(), sizeof(PointType),
+                                          transformTobeMapped, matP, &deg, LIOGPU_MAX_ITER, &lastInfo, &n_ds,
+                                          laserCloudSurfLastDS.data(), sizeof(PointType), (int)laserCloudSurfLastDS.size());
+  isDegenerate = deg != 0;
+  laserCloudSurfLastDS.resize(lastStatus < 0 ? 0 : n_ds);
+  laserCloudSurfLastDSNum = n_ds;
+}
+
+Cloud mapOptimization::transformPointCloud(const Cloud& in, const PointTypePose& p) {
+  Cloud out(in.size());
+  const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+  lastStatus = liogpu_transform_cloud(ctx_, in.data(), (int)in.size(), sizeof(PointType), pose6, out.data(), sizeof(PointType));
+  return out;
+}
+
+bool mapOptimization::saveFrame() const {  // :1909-1928 — relative motion since the last keyframe
+  if (cloudKeyPoses3D.empty()) return true;
+  const PointTypePose& k = cloudKeyPoses6D.back();
+  auto rot = [](float r, float p, float y, double R[9]) {
+    const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
+    R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = sy * sr + cy * sp * cr;
+    R[3] = sy * cp; R[4] = cy * cr + sy * sp * sr; R[5] = sy * sp * cr - cy * sr;
+    R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+  };
+  double A[9], B[9], D[9];
+  rot(k.roll, k.pitch, k.yaw, A);
+  rot(transformTobeMapped[0], transformTobeMapped[1], transformTobeMapped[2], B);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) D[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
+  const double dt[3] = {transformTobeMapped[3] - k.x, transformTobeMapped[4] - k.y, transformTobeMapped[5] - k.z};
+  double loc[3];
+  for (int i = 0; i < 3; ++i) loc[i] = A[0 * 3 + i] * dt[0] + A[1 * 3 + i] * dt[1] + A[2 * 3 + i] * dt[2];
+  const double roll = std::atan2(D[7], D[8]), pitch = std::asin(-D[6]), yaw = std::atan2(D[3], D[0]);
+  if (std::fabs(roll) < surroundingkeyframeAddingAngleThreshold && std::fabs(pitch) < surroundingkeyframeAddingAngleThreshold &&
+      std::fabs(yaw) < surroundingkeyframeAddingAngleThreshold &&
+      std::sqrt(loc[0] * loc[0] + loc[1] * loc[1] + loc[2] * loc[2]) < surroundingkeyframeAddingDistThreshold)
+    return false;
+  return true;
+}
+
+void mapOptimization::saveKeyFrame() {  // :2128-2142 without the factor graph
+  PointType p3{};
+  p3.x = transformTobeMapped[3]; p3.y = transformTobeMapped[4]; p3.z = transformTobeMapped[5];
+  p3.data3 = 1.0f;
+  p3.intensity = (float)cloudKeyPoses3D.size();
+  PointTypePose p6{};
+  p6.x = p3.x; p6.y = p3.y; p6.z = p3.z; p6.intensity = p3.intensity;
+  p6.roll = transformTobeMapped[0]; p6.pitch = transformTobeMapped[1]; p6.yaw = transformTobeMapped[2];
+  p6.time = timeLaserInfoCur;
+  // surfCloudKeyFrames.push_back(thisSurfKeyFrame): the downsampled sweep stays resident on the GPU
+  lastStatus = liogpu_keyframe_put(ctx_, (int)cloudKeyPoses3D.size(), laserCloudSurfLastDS.data(), (int)laserCloudSurfLastDS.size(),
+                                   sizeof(PointType));
+  cloudKeyPoses3D.push_back(p3);
+  cloudKeyPoses6D.push_back(p6);
+}
+
+}  // namespace liorf_gpu

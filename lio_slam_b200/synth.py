@@ -243,3 +243,30 @@ def make_imu_table(time_scan_cur: float, seed: int, rate_hz: float = 200.0, span
         ry[k] = ry[k - 1] + gy[k] * h
         rz[k] = rz[k - 1] + gz[k] * h
     return t, rx, ry, rz
+
+
+def write_sequence(path: str, world: World, beams: int, n_scans: int, seed: int, cols: int = 600, step: float = 0.35,
+                   guess_noise: float = 0.5):
+    """A replay file for lio_slam_b200/host/replay_driver.cpp: n_scans sweeps along the path; the initial
+    guess of each sweep is the ground truth perturbed like an IMU-odometry prediction (scan 0: exact).
+    Returns the ground-truth poses (n_scans, 6)."""
+    import struct
+    gts = []
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", n_scans))
+        for s in range(n_scans):
+            gt = path_pose(step * s)
+            gts.append(gt)
+            scan = xyzirt_to_xyzi(make_scan(world, gt, beams, seed * 100 + s, cols=cols))
+            scan_rec = np.zeros((scan.shape[0], 8), np.float32)
+            scan_rec[:, 0], scan_rec[:, 1], scan_rec[:, 2] = scan["x"], scan["y"], scan["z"]
+            scan_rec[:, 3] = 1.0
+            scan_rec[:, 4] = scan["intensity"]
+            guess = gt.astype(np.float32) if s == 0 else perturbed_guess(
+                gt, seed * 7 + s, rot_deg=(0.2 * guess_noise, 0.2 * guess_noise, 0.5 * guess_noise),
+                trans=(0.08 * guess_noise, 0.08 * guess_noise, 0.03 * guess_noise))
+            f.write(struct.pack("<d", 0.1 * s))
+            f.write(np.asarray(guess, np.float32).tobytes())
+            f.write(struct.pack("<i", scan_rec.shape[0]))
+            f.write(scan_rec.tobytes())
+    return np.array(gts)

@@ -353,7 +353,7 @@ def test_scan2map_full_size_properties(gpu):
     world = synth.make_world(1234)
     pose_gt = synth.path_pose(0.2)
     scan4 = synth.to_packed(synth.make_scan(world, pose_gt, 64, seed=31))
-    map4 = synth.make_local_map(world, 64, 200000, 0.3, seed=9, s0=-0.3)
+    map4 = synth.make_local_map(world, 64, 120000, 0.3, seed=9, s0=-0.3, max_poses=16)
     gpu.set_local_map(map4)
     ds, _ = gpu.voxel_downsample(scan4, 0.4)
     poses = []
@@ -367,3 +367,28 @@ def test_scan2map_full_size_properties(gpu):
     a = gpu.scan2map(ds, synth.perturbed_guess(pose_gt, 1))
     b = gpu.scan2map(ds, synth.perturbed_guess(pose_gt, 1))
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2]["JtJ"], b[2]["JtJ"])
+
+
+def test_replay_driver_tracks_ground_truth(world, tmp_path):
+    # the C++ host mirror (lio_slam_b200/host) driving the C ABI over a short sequence: keyframes are
+    # added by the reference's saveFrame rule, the local map is rebuilt from device-resident keyframes,
+    # and every registered pose stays near ground truth
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "lio_slam_b200", "replay_driver")
+    if not os.path.exists(exe):
+        pytest.skip("replay_driver not built")
+    seq = str(tmp_path / "seq.bin")
+    out = str(tmp_path / "poses.txt")
+    gts = synth.write_sequence(seq, world, 16, 14, seed=3)
+    r = subprocess.run([exe, seq, out, "0", "0.4", "0.5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    rows = np.loadtxt(out)
+    assert rows.shape[0] == 14 and summary["keyframes"] >= 3 and summary["registered"] == 13
+    poses = rows[:, 1:7]
+    assert np.abs(poses[:, 3:] - gts[:, 3:]).max() < 0.08 and np.abs(poses[:, :3] - gts[:, :3]).max() < 0.01
+    assert (rows[1:, 7] >= 1).all() and (rows[1:, 8] > 500).all()
+    print(summary)
