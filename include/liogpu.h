@@ -61,7 +61,8 @@ typedef struct liogpu_params {
   float knn_cell_size;       /* edge of the sorted-grid cell used for the 5-NN index; 0 = auto   */
   float knn_phase1_radius;   /* radius of the cheap first search phase; 0 = auto (2 x map leaf),
                                 < 0 = single phase.  Tuning only: results do not depend on it.   */
-  int reserved[6];
+  int profile_kernels;       /* 1: time every kernel of the LM loop with CUDA events (bench.py)  */
+  int reserved[5];
 } liogpu_params;
 
 /* Result block of liogpu_scan2map (everything the reference keeps in members after the loop). */
@@ -81,6 +82,11 @@ typedef struct liogpu_s2m_info {
   float pose_hist[LIOGPU_MAX_ITER][6]; /* transformTobeMapped after each executed iteration        */
   int nsel_hist[LIOGPU_MAX_ITER];
   float gpu_ms;      /* device time of the loop (CUDA events on the context's stream)              */
+  int seeded;        /* last iteration: points whose search started from the previous neighbours   */
+  /* filled only when params.profile_kernels != 0 (CUDA events around every launch of the first chunk): */
+  float main_kernel_ms;   /* summed device time of s2m_main_kernel over the executed iterations    */
+  float left_kernel_ms;   /* summed device time of s2m_left_kernel over the executed iterations    */
+  int main_kernel_launches, left_kernel_launches; /* executed (not early-exit) launches timed      */
 } liogpu_s2m_info;
 
 int liogpu_abi_version(void);

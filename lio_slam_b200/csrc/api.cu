@@ -119,7 +119,12 @@ int liogpu_create(liogpu_ctx** out, const liogpu_params* params) {
   c.prm = *params;
   c.device = params->device;
   c.sm_count = prop.multiProcessorCount;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c.side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.ev_it0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess ||
       cudaHostAlloc(&c.h_pinned, 131072, cudaHostAllocDefault) != cudaSuccess) {
     liogpu_destroy(ctx);
@@ -138,15 +143,20 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   Ctx& c = ctx->c;
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
+  if (c.side_stream) cudaStreamSynchronize(c.side_stream);
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.fail_buf, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
+                    &c.fail_buf, &c.prev_nn, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
   for (DevBuf* b : bufs) b->release();
   for (auto& kv : c.keyframes) kv.second.first.release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
+  for (cudaEvent_t e : c.prof_ev) cudaEventDestroy(e);
+  if (c.ev_it0) cudaEventDestroy(c.ev_it0);
+  if (c.ev_side) cudaEventDestroy(c.ev_side);
+  if (c.side_stream) cudaStreamDestroy(c.side_stream);
   if (c.stream) cudaStreamDestroy(c.stream);
   delete ctx;
 }

@@ -78,6 +78,11 @@ struct LmDevState {
   double Jtr[6];
   float pose_hist[LIOGPU_MAX_ITER][6];
   int nsel_hist[LIOGPU_MAX_ITER];
+  // iteration-0 eigen analysis moved off the critical path (s2m.cu: lm_matp_kernel)
+  float AtA0[36];     // AtA of iteration 0 (f32, as cv::eigen sees it)
+  int eig_pending;    // 1: matP still has to be computed from AtA0 by lm_matp_kernel
+  int cert_mismatch;  // must stay 0: the side computation contradicted the non-degeneracy certificate
+  int seeded;         // points of the last executed iteration that started from the previous neighbours
 };
 
 // host-visible context
@@ -86,6 +91,9 @@ struct Ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // iteration-0 eigen analysis, overlapped with iterations 1..
+  cudaEvent_t ev_it0 = nullptr, ev_side = nullptr;
+  std::vector<cudaEvent_t> prof_ev;  // params.profile_kernels: 3 events per iteration of a chunk
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   unsigned long long launches = 0;
@@ -103,7 +111,7 @@ struct Ctx {
   // sort + scan scratch
   DevBuf keys0, keys1, vals0, vals1, counters, scan_tmp, seg_flag, seg_start;
   // small device structs
-  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf;
+  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf, prev_nn;
   // per-point debug outputs of surf_optimization
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
   // pinned host mirrors

@@ -209,176 +209,12 @@ __device__ __forceinline__ void jacobian_row(const LmTrig g, const float4 o, con
   rhs = -c.w;
 }
 
-// ---- OpenCV 4.x 6x6 pieces, single thread, row-major ----
-// cv::solve(AtA, AtB, X, DECOMP_QR) (:1784): hal::QR32f Householder, eps = 10*FLT_EPSILON.
-static __device__ __noinline__ bool solve6_qr(const float* Ain, const float* bin, float* x) {
-  const float eps = FLT_EPSILON * 10;
-  float A[36], b[6], vl[6], hf[6];
-  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
-  for (int i = 0; i < 6; ++i) b[i] = bin[i];
-  for (int l = 0; l < 6; ++l) {
-    const int vs = 6 - l;
-    float vn = 0.f;
-    for (int i = 0; i < vs; ++i) { vl[i] = A[(l + i) * 6 + l]; vn += vl[i] * vl[i]; }
-    const float t0 = vl[0];
-    vl[0] = vl[0] + (vl[0] >= 0.f ? 1.f : -1.f) * sqrtf(vn);
-    vn = sqrtf(vn + vl[0] * vl[0] - t0 * t0);
-    for (int i = 0; i < vs; ++i) vl[i] /= vn;
-    for (int j = l; j < 6; ++j) {
-      float va = 0.f;
-      for (int i = l; i < 6; ++i) va += vl[i - l] * A[i * 6 + j];
-      for (int i = l; i < 6; ++i) A[i * 6 + j] -= 2 * vl[i - l] * va;
-    }
-    hf[l] = vl[0] * vl[0];
-    for (int i = 1; i < vs; ++i) A[(l + i) * 6 + l] = vl[i] / vl[0];
-  }
-  for (int l = 0; l < 6; ++l) {
-    vl[0] = 1.f;
-    for (int j = 1; j < 6 - l; ++j) vl[j] = A[(j + l) * 6 + l];
-    float vb = 0.f;
-    for (int i = l; i < 6; ++i) vb += vl[i - l] * b[i];
-    for (int i = l; i < 6; ++i) b[i] -= 2 * vl[i - l] * vb * hf[l];
-  }
-  for (int i = 5; i >= 0; --i) {
-    for (int j = 5; j > i; --j) b[i] -= b[j] * A[i * 6 + j];
-    if (fabsf(A[i * 6 + i]) < eps) {
-      for (int k = 0; k < 6; ++k) x[k] = 0.f;
-      return false;
-    }
-    b[i] /= A[i * 6 + i];
-  }
-  for (int i = 0; i < 6; ++i) x[i] = b[i];
-  return true;
-}
-
+// ---- OpenCV 4.x 6x6 pieces: the solve / eigen / inverse routines live in s2m.cu ----
 __device__ __forceinline__ float cv_hypotf(float a, float b) {
   a = fabsf(a); b = fabsf(b);
   if (a > b) { b /= a; return a * sqrtf(1 + b * b); }
   if (b > 0) { a /= b; return b * sqrtf(1 + a * a); }
   return 0.f;
-}
-
-// cv::eigen(matAtA, matE, matV) (:1792): JacobiImpl_<float>; eigenvalues descending, eigenvectors as rows.
-static __device__ __noinline__ void eigen6_jacobi(const float* Ain, float* W, float* V) {
-  const int n = 6;
-  float A[36];
-  int indR[6], indC[6];
-  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
-  for (int i = 0; i < n; ++i) {
-    for (int j = 0; j < n; ++j) V[i * 6 + j] = 0.f;
-    V[i * 6 + i] = 1.f;
-  }
-  int i, j, k, m;
-  float mv = 0.f;
-  for (k = 0; k < n; ++k) {
-    W[k] = A[7 * k];
-    if (k < n - 1) {
-      for (m = k + 1, mv = fabsf(A[6 * k + m]), i = k + 2; i < n; ++i) {
-        const float val = fabsf(A[6 * k + i]);
-        if (mv < val) { mv = val; m = i; }
-      }
-      indR[k] = m;
-    }
-    if (k > 0) {
-      for (m = 0, mv = fabsf(A[k]), i = 1; i < k; ++i) {
-        const float val = fabsf(A[6 * i + k]);
-        if (mv < val) { mv = val; m = i; }
-      }
-      indC[k] = m;
-    }
-  }
-  for (int it = 0; it < n * n * 30; ++it) {
-    for (k = 0, mv = fabsf(A[indR[0]]), i = 1; i < n - 1; ++i) {
-      const float val = fabsf(A[6 * i + indR[i]]);
-      if (mv < val) { mv = val; k = i; }
-    }
-    int l = indR[k];
-    for (i = 1; i < n; ++i) {
-      const float val = fabsf(A[6 * indC[i] + i]);
-      if (mv < val) { mv = val; k = indC[i]; l = i; }
-    }
-    const float p = A[6 * k + l];
-    if (fabsf(p) <= FLT_EPSILON) break;
-    const float y = (float)((W[l] - W[k]) * 0.5);
-    float t = fabsf(y) + cv_hypotf(p, y);
-    float s = cv_hypotf(p, t);
-    const float c = t / s;
-    s = p / s;
-    t = (p / t) * p;
-    if (y < 0) { s = -s; t = -t; }
-    A[6 * k + l] = 0;
-    W[k] -= t;
-    W[l] += t;
-    float a0, b0;
-#define LIOGPU_ROT(v0, v1) { a0 = v0; b0 = v1; v0 = a0 * c - b0 * s; v1 = a0 * s + b0 * c; }
-    for (i = 0; i < k; ++i) LIOGPU_ROT(A[6 * i + k], A[6 * i + l])
-    for (i = k + 1; i < l; ++i) LIOGPU_ROT(A[6 * k + i], A[6 * i + l])
-    for (i = l + 1; i < n; ++i) LIOGPU_ROT(A[6 * k + i], A[6 * l + i])
-    for (i = 0; i < n; ++i) LIOGPU_ROT(V[6 * k + i], V[6 * l + i])
-#undef LIOGPU_ROT
-    for (j = 0; j < 2; ++j) {
-      const int idx = j == 0 ? k : l;
-      if (idx < n - 1) {
-        for (m = idx + 1, mv = fabsf(A[6 * idx + m]), i = idx + 2; i < n; ++i) {
-          const float val = fabsf(A[6 * idx + i]);
-          if (mv < val) { mv = val; m = i; }
-        }
-        indR[idx] = m;
-      }
-      if (idx > 0) {
-        for (m = 0, mv = fabsf(A[idx]), i = 1; i < idx; ++i) {
-          const float val = fabsf(A[6 * i + idx]);
-          if (mv < val) { mv = val; m = i; }
-        }
-        indC[idx] = m;
-      }
-    }
-  }
-  for (k = 0; k < n - 1; ++k) {
-    m = k;
-    for (i = k + 1; i < n; ++i)
-      if (W[m] < W[i]) m = i;
-    if (k != m) {
-      const float tw = W[m]; W[m] = W[k]; W[k] = tw;
-      for (i = 0; i < n; ++i) { const float tv = V[6 * m + i]; V[6 * m + i] = V[6 * k + i]; V[6 * k + i] = tv; }
-    }
-  }
-}
-
-// matV.inv() (:1807): cv::invert DECOMP_LU -> hal::LU32f on [A | I], partial pivoting.
-static __device__ __noinline__ bool inv6_lu(const float* Ain, float* b) {
-  const int m = 6;
-  const float eps = FLT_EPSILON * 10;
-  float A[36];
-  for (int i = 0; i < 36; ++i) A[i] = Ain[i];
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j < 6; ++j) b[i * 6 + j] = i == j ? 1.f : 0.f;
-  for (int i = 0; i < m; ++i) {
-    int k = i;
-    for (int j = i + 1; j < m; ++j)
-      if (fabsf(A[j * 6 + i]) > fabsf(A[k * 6 + i])) k = j;
-    if (fabsf(A[k * 6 + i]) < eps) {
-      for (int q = 0; q < 36; ++q) b[q] = 0.f;
-      return false;
-    }
-    if (k != i) {
-      for (int j = i; j < m; ++j) swapf(A[i * 6 + j], A[k * 6 + j]);
-      for (int j = 0; j < m; ++j) swapf(b[i * 6 + j], b[k * 6 + j]);
-    }
-    const float d = -1 / A[i * 6 + i];
-    for (int j = i + 1; j < m; ++j) {
-      const float alpha = A[j * 6 + i] * d;
-      for (int q = i + 1; q < m; ++q) A[j * 6 + q] += alpha * A[i * 6 + q];
-      for (int q = 0; q < m; ++q) b[j * 6 + q] += alpha * b[i * 6 + q];
-    }
-  }
-  for (int i = m - 1; i >= 0; --i)
-    for (int j = 0; j < m; ++j) {
-      float s = b[i * 6 + j];
-      for (int k = i + 1; k < m; ++k) s -= A[i * 6 + k] * b[k * 6 + j];
-      b[i * 6 + j] = s / A[i * 6 + i];
-    }
-  return true;
 }
 
 }  // namespace liogpu

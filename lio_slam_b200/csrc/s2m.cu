@@ -253,50 +253,65 @@ struct FinSmem {
 };
 constexpr unsigned FULL = 0xffffffffu;
 
-// cv::solve(AtA, AtB, X, DECOMP_QR) (:1784) — hal::QR32f Householder.  Lane j owns column j.
-__device__ __forceinline__ void warp_solve6_qr(FinSmem& m, const int lane) {
-  for (int e = lane; e < 36; e += 32) m.QA[e] = m.AtA[e];
-  if (lane < 6) m.qb[lane] = m.AtB[lane];
-  __syncwarp();
-  for (int l = 0; l < 6; ++l) {
-    const int vs = 6 - l;
-    float v = lane < vs ? m.QA[(l + lane) * 6 + l] : 0.f;
-    const float sq = v * v;
-    float vn = 0.f;
-    for (int i = 0; i < vs; ++i) vn += __shfl_sync(FULL, sq, i);  // sequential order of the reference
-    const float t0 = __shfl_sync(FULL, v, 0);
-    const float v0 = t0 + (t0 >= 0.f ? 1.f : -1.f) * sqrtf(vn);
-    const float vn2 = sqrtf(vn + v0 * v0 - t0 * t0);
-    if (lane == 0) v = v0;
-    v = v / vn2;
-    if (lane < vs) m.vl[lane] = v;
-    __syncwarp();
-    if (lane >= l && lane < 6) {  // column j = lane
-      float va = 0.f;
-      for (int i = l; i < 6; ++i) va += m.vl[i - l] * m.QA[i * 6 + lane];
-      for (int i = l; i < 6; ++i) m.QA[i * 6 + lane] -= 2 * m.vl[i - l] * va;
-    }
-    __syncwarp();
-    if (lane == 0) m.hf[l] = m.vl[0] * m.vl[0];
-    if (lane >= 1 && lane < vs) m.QA[(l + lane) * 6 + l] = m.vl[lane] / m.vl[0];
-    __syncwarp();
+// cv::solve(AtA, AtB, X, DECOMP_QR) (:1784) — hal::QR32f Householder (no pivoting), executed by ONE lane
+// with every loop fully unrolled: all indices are compile-time constants, so the 6x6 matrix, the rhs and the
+// reflector live in registers and the ~600 f32 operations run as straight-line code (about 1 us), in
+// exactly the operation order of OpenCV's QRImpl.  (A warp-parallel version over shared memory was 5x
+// slower: every step paid a shared-memory round trip and a __syncwarp.)
+__device__ __forceinline__ void solve6_qr_reg(const float* __restrict__ Ain, const float* __restrict__ bin,
+                                              float* __restrict__ x) {
+  const float eps = FLT_EPSILON * 10;
+  float A[6][6], b[6], hf[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) A[i][j] = Ain[i * 6 + j];
+    b[i] = bin[i];
   }
+#pragma unroll
+  for (int l = 0; l < 6; ++l) {
+    float vl[6];
+    float vn = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6 - l; ++i) { vl[i] = A[l + i][l]; vn += vl[i] * vl[i]; }
+    const float t0 = vl[0];
+    vl[0] = vl[0] + (vl[0] >= 0.f ? 1.f : -1.f) * sqrtf(vn);
+    vn = sqrtf(vn + vl[0] * vl[0] - t0 * t0);
+#pragma unroll
+    for (int i = 0; i < 6 - l; ++i) vl[i] /= vn;
+#pragma unroll
+    for (int j = l; j < 6; ++j) {
+      float va = 0.f;
+#pragma unroll
+      for (int i = l; i < 6; ++i) va += vl[i - l] * A[i][j];
+#pragma unroll
+      for (int i = l; i < 6; ++i) A[i][j] -= 2 * vl[i - l] * va;
+    }
+    hf[l] = vl[0] * vl[0];
+#pragma unroll
+    for (int i = 1; i < 6 - l; ++i) A[l + i][l] = vl[i] / vl[0];
+  }
+#pragma unroll
   for (int l = 0; l < 6; ++l) {
     float vb = 0.f;
-    for (int i = l; i < 6; ++i) vb += (i == l ? 1.f : m.QA[i * 6 + l]) * m.qb[i];
-    __syncwarp();
-    if (lane >= l && lane < 6) m.qb[lane] -= 2 * (lane == l ? 1.f : m.QA[lane * 6 + l]) * vb * m.hf[l];
-    __syncwarp();
+#pragma unroll
+    for (int i = l; i < 6; ++i) vb += (i == l ? 1.f : A[i][l]) * b[i];
+#pragma unroll
+    for (int i = l; i < 6; ++i) b[i] -= 2 * (i == l ? 1.f : A[i][l]) * vb * hf[l];
   }
-  if (lane == 0) {
-    bool ok = true;
-    for (int i = 5; i >= 0 && ok; --i) {
-      for (int j = 5; j > i; --j) m.qb[i] -= m.qb[j] * m.QA[i * 6 + j];
-      if (fabsf(m.QA[i * 6 + i]) < FLT_EPSILON * 10) { ok = false; break; }
-      m.qb[i] /= m.QA[i * 6 + i];
-    }
-    for (int i = 0; i < 6; ++i) m.X[i] = ok ? m.qb[i] : 0.f;
+  bool ok = true;
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+#pragma unroll
+    for (int j = 5; j > i; --j) b[i] -= b[j] * A[i][j];
+    if (fabsf(A[i][i]) < eps) ok = false;  // cv::solve returns false; the reference ignores it and X stays 0
+    b[i] /= A[i][i];
   }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = ok ? b[i] : 0.f;
+}
+__device__ __forceinline__ void warp_solve6_qr(FinSmem& m, const int lane) {
+  if (lane == 0) solve6_qr_reg(m.AtA, m.AtB, m.X);
   __syncwarp();
 }
 
@@ -439,32 +454,132 @@ __device__ __forceinline__ void warp_inv6_lu(FinSmem& m, const int lane) {
 
 // transPointAssociateToMap and the LM trig terms of the current pose, computed ONCE per iteration
 // instead of once per thread block; lanes 0-2 evaluate the f64 sin/cos of roll, pitch, yaw in parallel.
-__device__ __forceinline__ void warp_refresh_transform(LmDevState* st, const int lane) {
+__device__ __forceinline__ void warp_refresh_transform(LmDevState* st, const int lane, const float pose_l) {
+  // pose_l: lane k < 6 holds pose[k] = {roll, pitch, yaw, x, y, z}
   float sn = 0.f, cs = 0.f;
   if (lane < 3) {
-    const double a = (double)st->pose[lane];
+    const double a = (double)pose_l;
     sn = (float)sin(a);
     cs = (float)cos(a);
   }
   const float F = __shfl_sync(FULL, sn, 0), E = __shfl_sync(FULL, cs, 0);  // roll
   const float D = __shfl_sync(FULL, sn, 1), C = __shfl_sync(FULL, cs, 1);  // pitch
   const float B = __shfl_sync(FULL, sn, 2), A = __shfl_sync(FULL, cs, 2);  // yaw
+  const float px = __shfl_sync(FULL, pose_l, 3), py = __shfl_sync(FULL, pose_l, 4), pz = __shfl_sync(FULL, pose_l, 5);
   if (lane == 0) {  // pcl::getTransformation — same products as pose_to_T
     const float DE = D * E, DF = D * F;
     float* T = st->T;
-    T[0] = A * C;  T[1] = A * DF - B * E;  T[2] = B * F + A * DE;  T[3] = st->pose[3];
-    T[4] = B * C;  T[5] = A * E + B * DF;  T[6] = B * DE - A * F;  T[7] = st->pose[4];
-    T[8] = -D;     T[9] = C * F;           T[10] = C * E;          T[11] = st->pose[5];
+    T[0] = A * C;  T[1] = A * DF - B * E;  T[2] = B * F + A * DE;  T[3] = px;
+    T[4] = B * C;  T[5] = A * E + B * DF;  T[6] = B * DE - A * F;  T[7] = py;
+    T[8] = -D;     T[9] = C * F;           T[10] = C * E;          T[11] = pz;
     // srx,crx = sin,cos(yaw); sry,cry = (pitch); srz,crz = (roll)  (:1714-1719)
     st->trig[0] = B; st->trig[1] = A; st->trig[2] = D; st->trig[3] = C; st->trig[4] = F; st->trig[5] = E;
   }
 }
 __global__ void lm_prepare_kernel(LmDevState* st) {
-  if (blockIdx.x == 0 && threadIdx.x < 32) warp_refresh_transform(st, threadIdx.x);
+  if (blockIdx.x == 0 && threadIdx.x < 32) warp_refresh_transform(st, threadIdx.x, threadIdx.x < 6 ? st->pose[threadIdx.x] : 0.f);
+}
+
+// lambda_min(A) > mu  <=>  A - mu*I is positive definite  <=>  its LDL^T has positive pivots (f64, static
+// indices: everything stays in registers).  mu = 100 + 1e-4 * trace(A).
+__device__ __forceinline__ bool certify_min_eig(const float* A32) {
+  double a[6][6];
+  double tr = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) tr += (double)A32[i * 6 + i];
+  if (!(tr > 0)) return false;
+  const double mu = 100.0 + 1e-4 * tr;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[i][j] = (double)A32[i * 6 + j] - (i == j ? mu : 0.0);
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double piv = a[k][k];
+    if (!(piv > 1e-3 * mu)) ok = false;  // also rejects NaN; keeps a margin against cancellation
+    const double inv = 1.0 / piv;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = a[i][k] * inv;
+#pragma unroll
+      for (int j = k + 1; j <= i; ++j) a[i][j] -= f * a[j][k];
+    }
+  }
+  return ok;
+}
+
+// cv::eigen + the degeneracy loop + matP = matV.inv() * matV2 (:1792-1808), one warp; writes st->degenerate
+__device__ __forceinline__ int eigen_matP(LmDevState* st, FinSmem& m, const int lane, float* matP_out) {
+  warp_eigen6(m, lane);
+  for (int e = lane; e < 36; e += 32) m.V2[e] = m.V[e];
+  __syncwarp();
+  int deg = 0;
+  if (lane == 0) {
+    for (int i = 5; i >= 0; --i) {
+      if (m.W[i] < 100.f) {
+        for (int j = 0; j < 6; ++j) m.V2[i * 6 + j] = 0.f;
+        deg = 1;
+      } else {
+        break;
+      }
+    }
+  }
+  deg = __shfl_sync(FULL, deg, 0);
+  __syncwarp();
+  warp_inv6_lu(m, lane);
+  for (int e = lane; e < 36; e += 32) {  // f64 accumulation, as cv::gemm does
+    const int i = e / 6, j = e % 6;
+    double acc = 0;
+    for (int k = 0; k < 6; ++k) acc += (double)m.Vi[i * 6 + k] * (double)m.V2[k * 6 + j];
+    matP_out[e] = (float)acc;
+  }
+  if (lane == 0) st->degenerate = deg;
+  return deg;
+}
+
+// Side computation of iteration 0's matP when the certificate let the loop go ahead (second stream).
+__global__ void lm_matp_kernel(LmDevState* st) {
+  __shared__ FinSmem m;
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0 || lane >= 32) return;
+  if (!st->eig_pending) return;
+  for (int e = lane; e < 36; e += 32) m.AtA[e] = st->AtA0[e];
+  __syncwarp();
+  // st->degenerate is not touched here: iterations 1.. read it concurrently
+  warp_eigen6(m, lane);
+  for (int e = lane; e < 36; e += 32) m.V2[e] = m.V[e];
+  __syncwarp();
+  int deg = 0;
+  if (lane == 0) {
+    for (int i = 5; i >= 0; --i) {
+      if (m.W[i] < 100.f) {
+        for (int j = 0; j < 6; ++j) m.V2[i * 6 + j] = 0.f;
+        deg = 1;
+      } else {
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  warp_inv6_lu(m, lane);
+  for (int e = lane; e < 36; e += 32) {
+    const int i = e / 6, j = e % 6;
+    double acc = 0;
+    for (int k = 0; k < 6; ++k) acc += (double)m.Vi[i * 6 + k] * (double)m.V2[k * 6 + j];
+    st->matP[e] = (float)acc;
+  }
+  if (lane == 0) {
+    if (deg) st->cert_mismatch = 1;  // cannot happen: the certificate is 1000+ ulps away from the threshold
+    st->eig_pending = 0;
+  }
 }
 
 __device__ __noinline__ void lm_finalize_warp(LmDevState* st, const double* sums, FinSmem& m, const int lane) {
-  const int it = st->iter;
+  // one batch of loads for every state field the tail needs (instead of a chain of dependent L2 reads)
+  float pose_l = lane < 6 ? st->pose[lane] : 0.f;
+  const int it = st->iter, max_iter = st->max_iter;
+  int degenerate = st->degenerate;
   const int nsel = (int)sums[27];
   // expand the upper triangle; AtA(a,b) and AtA(b,a) are the same f64 sum of the same products
   for (int e = lane; e < 36; e += 32) {
@@ -475,45 +590,39 @@ __device__ __noinline__ void lm_finalize_warp(LmDevState* st, const double* sums
     m.AtA[e] = (float)v;
   }
   if (lane < 6) { st->Jtr[lane] = sums[21 + lane]; m.AtB[lane] = (float)sums[21 + lane]; }
-  if (lane == 0) { st->n_sel = nsel; st->tie_queries = (int)sums[28]; st->nsel_hist[it] = nsel; }
+  if (lane == 0) { st->n_sel = nsel; st->tie_queries = (int)sums[28]; st->nsel_hist[it] = nsel; st->seeded = (int)sums[29]; }
   __syncwarp();
   bool conv = false;
   if (nsel >= 50) {  // :1721-1724 — below 50 the pose is untouched and the loop just repeats
     warp_solve6_qr(m, lane);
     if (it == 0) {  // :1786-1808
-      warp_eigen6(m, lane);
-      for (int e = lane; e < 36; e += 32) m.V2[e] = m.V[e];
-      __syncwarp();
-      if (lane == 0) {
-        int deg = 0;
-        for (int i = 5; i >= 0; --i) {
-          if (m.W[i] < 100.f) {
-            for (int j = 0; j < 6; ++j) m.V2[i * 6 + j] = 0.f;
-            deg = 1;
-          } else {
-            break;
-          }
-        }
-        st->degenerate = deg;
-      }
-      __syncwarp();
-      warp_inv6_lu(m, lane);
-      for (int e = lane; e < 36; e += 32) {  // matP = matV.inv() * matV2 (f64 accumulation, cv::gemm)
-        const int i = e / 6, j = e % 6;
-        double acc = 0;
-        for (int k = 0; k < 6; ++k) acc += (double)m.Vi[i * 6 + k] * (double)m.V2[k * 6 + j];
-        st->matP[e] = (float)acc;
+      // cv::eigen (a few hundred dependent steps) is only needed to DECIDE isDegenerate and, if so, to
+      // build matP.  A rigorous certificate settles the common case at once: if AtA - mu*I is positive
+      // definite (LDL^T in f64, mu = 100 + 1e-4*trace, i.e. >1000 f32 ulps of ||AtA|| above the threshold)
+      // every eigenvalue OpenCV's f32 Jacobi can report is >= 100, so isDegenerate = false and matP is not
+      // read by this scan.  The exact matP (= V^-1 * V2) is then computed from the saved AtA by
+      // lm_matp_kernel on a second stream while iterations 1.. run; otherwise the exact path runs here.
+      bool certified = false;
+      if (lane == 0) certified = certify_min_eig(m.AtA);
+      certified = __shfl_sync(FULL, (int)certified, 0) != 0;
+      for (int e = lane; e < 36; e += 32) st->AtA0[e] = m.AtA[e];
+      if (certified) {
+        degenerate = 0;
+        if (lane == 0) { st->degenerate = 0; st->eig_pending = 1; }
+      } else {
+        degenerate = eigen_matP(st, m, lane, st->matP);
       }
       __threadfence_block();
       __syncwarp();
     }
     float xi = lane < 6 ? m.X[lane] : 0.f;
-    if (st->degenerate && lane < 6) {  // :1810-1815
+    if (degenerate && lane < 6) {  // :1810-1815
       double acc = 0;
       for (int k = 0; k < 6; ++k) acc += (double)st->matP[lane * 6 + k] * (double)m.X[k];
       xi = (float)acc;
     }
-    if (lane < 6) st->pose[lane] += xi;
+    pose_l += xi;
+    if (lane < 6) st->pose[lane] = pose_l;
     const float r2d = 57.29578f;  // pcl::rad2deg(float)
     const float x0 = __shfl_sync(FULL, xi, 0), x1 = __shfl_sync(FULL, xi, 1), x2 = __shfl_sync(FULL, xi, 2);
     const float x3 = __shfl_sync(FULL, xi, 3), x4 = __shfl_sync(FULL, xi, 4), x5 = __shfl_sync(FULL, xi, 5);
@@ -524,21 +633,19 @@ __device__ __noinline__ void lm_finalize_warp(LmDevState* st, const double* sums
     if (lane == 0) { st->delta_r = dr; st->delta_t = dt; }
     conv = ((double)dr < 0.05) && ((double)dt < 0.05);
   }
-  __syncwarp();
-  if (lane < 6) st->pose_hist[it][lane] = st->pose[lane];
+  if (lane < 6) st->pose_hist[it][lane] = pose_l;
   int iter = it + 1;
   if (nsel < 50) {
     // Nothing changed, so every remaining iteration of the reference's loop would redo identical work
     // and bail out at :1722 again (quirk q2): record them and stop instead of burning launches.
-    for (int k = it + 1; k < st->max_iter; ++k) {
-      if (lane < 6) st->pose_hist[k][lane] = st->pose[lane];
+    for (int k = it + 1; k < max_iter; ++k) {
+      if (lane < 6) st->pose_hist[k][lane] = pose_l;
       if (lane == 0) st->nsel_hist[k] = nsel;
     }
-    iter = st->max_iter;
+    iter = max_iter;
   }
-  const bool done = conv || iter >= st->max_iter;
-  __syncwarp();
-  if (!done) warp_refresh_transform(st, lane);
+  const bool done = conv || iter >= max_iter;
+  if (!done) warp_refresh_transform(st, lane, pose_l);
   if (lane == 0) {
     st->iter = iter;
     if (conv) st->converged = 1;
@@ -578,6 +685,7 @@ struct S2mArgs {
   SurfDebugOut dbg;
   int mode;
   int main_blocks;
+  int* prev_nn;            // [5][nq] neighbours found by the previous iteration (-1: none), SoA
 };
 
 struct RowAcc {  // which product of the staged row a reducing thread owns
@@ -615,6 +723,13 @@ __device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, cons
     if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (flag) jacobian_row(trig, ori, coeff, row, rhs);
+  if (A.mode == 0) {  // seeds of the next iteration
+    A.prev_nn[i] = found ? t.i(t.k0) : -1;
+    A.prev_nn[(size_t)A.nq + i] = t.i(t.k1);
+    A.prev_nn[2 * (size_t)A.nq + i] = t.i(t.k2);
+    A.prev_nn[3 * (size_t)A.nq + i] = t.i(t.k3);
+    A.prev_nn[4 * (size_t)A.nq + i] = t.i(t.k4);
+  }
   if (A.mode == 1) {
     if (A.dbg.nn_idx) {
       int* o = A.dbg.nn_idx + (size_t)i * 5;
@@ -637,32 +752,60 @@ s2m_main_kernel(const S2mArgs A) {
   __shared__ LmTrig sTrig;
   __shared__ float rows[S2M_THREADS][8];  // 6 Jacobian entries, rhs, accepted flag
   __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
-  __shared__ int s_ties, s_wfail[S2M_THREADS / 32];
+  __shared__ int s_ties, s_wfail[S2M_THREADS / 32], s_iter, s_seeded;
   __shared__ bool s_last;
 
-  if (A.mode == 0 && A.st->done) return;
+  __shared__ int s_done0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
   if (tid == 32) {
     sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
     sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
     s_ties = 0;
+    s_seeded = 0;
   }
+  if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
   __syncthreads();
+  if (A.mode == 0 && s_done0) return;
 
   const int i = blockIdx.x * S2M_THREADS + tid;
   float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float rhs = 0.f;
   bool flag = false, tie = false, need2 = false;
+  int seeded = 0;
   if (i < A.nq) {
     const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
     Top5 t;
-    if (A.g.gate1_d2 < A.g.gate_d2) {
-      grid_knn5(sel, A.g, A.g.gate1_d2, A.map_sorted, A.cell_start, t);
-      need2 = !(t.d(t.k4) < A.g.gate1_d2);
-    } else {
-      need2 = true;
+    bool searched = false;
+    if (s_iter > 0) {
+      // Seeded search: the five neighbours of the previous iteration are real map points, so their
+      // largest distance to the moved query bounds the true 5th-neighbour distance.  Searching inside
+      // that bound is exact, prunes almost every row, and needs no second phase.
+      const int p0 = A.prev_nn[i];
+      if (p0 >= 0) {
+        const int p1 = A.prev_nn[(size_t)A.nq + i], p2 = A.prev_nn[2 * (size_t)A.nq + i];
+        const int p3 = A.prev_nn[3 * (size_t)A.nq + i], p4 = A.prev_nn[4 * (size_t)A.nq + i];
+        float D = l2_simple(sel, __ldg(A.map4 + p0));
+        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p1)));
+        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p2)));
+        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p3)));
+        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p4)));
+        const float bound = __uint_as_float(__float_as_uint(D) + 1u);  // next float above D: the seeds stay inside
+        if (bound <= A.g.gate_d2) {
+          grid_knn5(sel, A.g, bound, A.map_sorted, A.cell_start, t);
+          searched = true;
+          ++seeded;
+        }
+      }
+    }
+    if (!searched) {
+      if (A.g.gate1_d2 < A.g.gate_d2) {
+        grid_knn5(sel, A.g, A.g.gate1_d2, A.map_sorted, A.cell_start, t);
+        need2 = !(t.d(t.k4) < A.g.gate1_d2);
+      } else {
+        need2 = true;
+      }
     }
     if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
   }
@@ -674,6 +817,10 @@ s2m_main_kernel(const S2mArgs A) {
   rows[tid][6] = rhs;
   rows[tid][7] = flag ? 1.f : 0.f;
   if (flag && tie) atomicAdd(&s_ties, 1);
+  {
+    const int ws = __popc(__ballot_sync(0xffffffffu, seeded != 0));
+    if (lane == 0 && ws) atomicAdd(&s_seeded, ws);
+  }
   __syncthreads();
   if (need2) {
     int base = 0;
@@ -701,6 +848,7 @@ s2m_main_kernel(const S2mArgs A) {
 #pragma unroll
     for (int k = 0; k < S2M_THREADS / 32; ++k) sum += red[k][tid];
     if (tid == 28) sum = (double)s_ties;
+    if (tid == 29) sum = (double)s_seeded;
     A.partials_main[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
   }
   if (tid == 0) {
@@ -755,17 +903,28 @@ s2m_left_kernel(const S2mArgs A) {
   __shared__ bool s_last;
   __shared__ FinSmem s_fin;
 
-  if (A.mode == 0 && A.st->done) return;
+  __shared__ int s_done0, s_iter0, s_total0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // every global value the block needs is requested in one go (one L2 round trip instead of four)
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];
   if (tid == 32) {
     sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
     sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
     s_ties = 0;
   }
+  if (tid == 64) { s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = *A.fail_total; }
+  // the offsets of the per-block leftover segments, staged once: the binary search below then runs on
+  // shared memory instead of ten dependent L2 round trips
+  constexpr int OFF_CAP = 4096;
+  __shared__ int s_off[OFF_CAP];
+  const bool off_in_smem = A.main_blocks + 1 <= OFF_CAP;
+  if (off_in_smem)
+    for (int k = tid; k <= A.main_blocks; k += LEFT_THREADS) s_off[k] = A.fail_off[k];
   __syncthreads();
-  const bool all_points = !(A.g.gate1_d2 < A.g.gate_d2);  // single-phase: the main kernel did not run
-  const int total = all_points ? A.nq : *A.fail_total;
+  if (A.mode == 0 && s_done0) return;
+  // sparse map (no phase-1 gate): on iteration 0 (and in mode 1) the main kernel did not run at all
+  const bool all_points = !(A.g.gate1_d2 < A.g.gate_d2) && (A.mode == 1 || s_iter0 == 0);
+  const int total = all_points ? A.nq : s_total0;
   const int warps_per_grid = gridDim.x * (LEFT_THREADS / 32);
   // points per warp: as few as possible (each point is a serial chain of dependent look-ups, so spreading
   // them over all resident warps hides that latency), up to 32 when there are more points than warps
@@ -793,9 +952,10 @@ s2m_left_kernel(const S2mArgs A) {
           int lo = 0, hi = A.main_blocks;  // invariant: fail_off[lo] <= e < fail_off[hi]
           while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (__ldg(A.fail_off + mid) <= e) lo = mid; else hi = mid;
+            const int v = off_in_smem ? s_off[mid] : __ldg(A.fail_off + mid);
+            if (v <= e) lo = mid; else hi = mid;
           }
-          mine = A.fail_seg[(size_t)lo * S2M_THREADS + (e - __ldg(A.fail_off + lo))];
+          mine = A.fail_seg[(size_t)lo * S2M_THREADS + (e - (off_in_smem ? s_off[lo] : __ldg(A.fail_off + lo)))];
         }
       }
       float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
@@ -849,10 +1009,19 @@ s2m_left_kernel(const S2mArgs A) {
   if (!s_last) return;
   __threadfence();
   {  // fixed-order sum over the left blocks: 8 slices of blocks, then the slices
-    double a2 = 0.0;
-#pragma unroll 8
-    for (unsigned b = warp; b < gridDim.x; b += LEFT_THREADS / 32) a2 += __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
-    red[warp][lane] = a2;
+    // four independent accumulators: the loads of a group are in flight together (fixed order of additions)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    constexpr unsigned W = LEFT_THREADS / 32;
+    unsigned b = warp;
+    for (; b + 3 * W < gridDim.x; b += 4 * W) {
+      const double v0 = __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
+      const double v1 = __ldcg(A.partials_left + (size_t)(b + W) * S2M_SUMS + lane);
+      const double v2 = __ldcg(A.partials_left + (size_t)(b + 2 * W) * S2M_SUMS + lane);
+      const double v3 = __ldcg(A.partials_left + (size_t)(b + 3 * W) * S2M_SUMS + lane);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; b < gridDim.x; b += W) a0 += __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
+    red[warp][lane] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   if (tid < S2M_SUMS) {
@@ -876,7 +1045,9 @@ static int check_grid(Ctx* c) {
 // device scratch shared by both entry points
 static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& main_blocks, int& left_blocks) {
   main_blocks = div_up(n, S2M_THREADS);
-  left_blocks = c->sm_count * 2;  // two resident CTAs per SM; rounds cover anything beyond one batch per warp
+  // two CTAs per SM: a leftover point is a serial chain of dependent look-ups (~5 us), so they are spread
+  // over as many resident warps as possible (one point per warp up to 2368 points)
+  left_blocks = c->sm_count * 2;
   LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
   LIOGPU_CUDA_OK(c, c->partials.reserve(((size_t)main_blocks + left_blocks) * S2M_SUMS * sizeof(double)));
   LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)main_blocks * S2M_THREADS + 2 * (size_t)main_blocks + 64) * sizeof(int)));
@@ -896,6 +1067,8 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   A.block_nfail = A.fail_off + main_blocks + 1;
   A.fail_total = A.block_nfail + main_blocks;
   A.ticket = c->block_counter.as<unsigned>();
+  LIOGPU_CUDA_OK(c, c->prev_nn.reserve((size_t)5 * (size_t)(n > 0 ? n : 1) * sizeof(int)));
+  A.prev_nn = c->prev_nn.as<int>();
   A.T_override = nullptr;
   A.dbg = SurfDebugOut{nullptr, nullptr, nullptr, nullptr, nullptr};
   A.mode = 0;
@@ -929,20 +1102,50 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
   // pay a second round trip.
   const int S2M_CHUNK = 6;
   int launched = 0;
+  float prof_main_ms = 0.f, prof_left_ms = 0.f;
+  int prof_main_n = 0, prof_left_n = 0;
   for (;;) {
     const int todo = (max_iter - launched) < S2M_CHUNK ? (max_iter - launched) : S2M_CHUNK;
+    // on a sparse map (no phase-1 gate) iteration 0 has nothing for the main kernel to do, but from
+    // iteration 1 on the seeded search runs there
     const bool two_phase = A.g.gate1_d2 < A.g.gate_d2;
+    const bool prof = c->prm.profile_kernels != 0 && launched == 0;
+    if (prof && c->prof_ev.empty()) {
+      c->prof_ev.resize(3 * S2M_CHUNK);
+      for (cudaEvent_t& e : c->prof_ev) LIOGPU_CUDA_OK(c, cudaEventCreate(&e));
+    }
     for (int it = 0; it < todo; ++it) {
-      if (two_phase) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+      const bool first = launched + it == 0;
+      if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
+      if (two_phase || !first) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+      if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
       s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
+      if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 2], c->stream));
+      c->launches += (two_phase || !first) ? 2 : 1;
+      if (first) {  // iteration 0's eigen analysis / matP off the critical path
+        LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev_it0, c->stream));
+        LIOGPU_CUDA_OK(c, cudaStreamWaitEvent(c->side_stream, c->ev_it0, 0));
+        lm_matp_kernel<<<1, 32, 0, c->side_stream>>>(d);
+        c->launches++;
+        LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev_side, c->side_stream));
+      }
     }
     launched += todo;
-    c->launches += (two_phase ? 2 : 1) * todo;
     LIOGPU_CUDA_OK(c, cudaGetLastError());
     LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+    LIOGPU_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_side, 0));
     LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(LmDevState), cudaMemcpyDeviceToHost, c->stream));
     LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     LIOGPU_CUDA_OK(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (prof) {
+      for (int it = 0; it < todo && it < h->iter; ++it) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, c->prof_ev[3 * it], c->prof_ev[3 * it + 1]);
+        cudaEventElapsedTime(&b, c->prof_ev[3 * it + 1], c->prof_ev[3 * it + 2]);
+        if (two_phase || it > 0) { prof_main_ms += a; ++prof_main_n; }
+        prof_left_ms += b; ++prof_left_n;
+      }
+    }
     if (h->done || launched >= max_iter) break;
   }
   for (int k = 0; k < 6; ++k) pose_io[k] = h->pose[k];
@@ -962,7 +1165,11 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
     memcpy(info->pose_hist, h->pose_hist, sizeof(info->pose_hist));
     memcpy(info->nsel_hist, h->nsel_hist, sizeof(info->nsel_hist));
     info->gpu_ms = c->last_ms;
+    info->seeded = h->seeded;
+    info->main_kernel_ms = prof_main_ms; info->left_kernel_ms = prof_left_ms;
+    info->main_kernel_launches = prof_main_n; info->left_kernel_launches = prof_left_n;
   }
+  if (h->cert_mismatch) { c->err = "internal: eigen certificate contradicted by the exact computation"; return LIOGPU_E_INVALID; }
   return LIOGPU_OK;
 }
 

@@ -29,7 +29,7 @@ class Params(C.Structure):
                 ("downsample_rate", C.c_int), ("point_filter_num", C.c_int),
                 ("lidar_min_front", C.c_float), ("lidar_min_back", C.c_float), ("lidar_min_left", C.c_float),
                 ("lidar_min_right", C.c_float), ("lidar_max_range", C.c_float), ("lidar_max_intensity", C.c_float),
-                ("knn_cell_size", C.c_float), ("knn_phase1_radius", C.c_float), ("reserved", C.c_int * 6)]
+                ("knn_cell_size", C.c_float), ("knn_phase1_radius", C.c_float), ("profile_kernels", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class S2MInfo(C.Structure):
@@ -37,7 +37,8 @@ class S2MInfo(C.Structure):
                 ("is_degenerate", C.c_int), ("tie_queries", C.c_int), ("delta_r_deg", C.c_float),
                 ("delta_t_cm", C.c_float), ("JtJ", C.c_double * 36), ("Jtr", C.c_double * 6),
                 ("pose_hist", (C.c_float * 6) * LIOGPU_MAX_ITER), ("nsel_hist", C.c_int * LIOGPU_MAX_ITER),
-                ("gpu_ms", C.c_float)]
+                ("gpu_ms", C.c_float), ("seeded", C.c_int), ("main_kernel_ms", C.c_float),
+                ("left_kernel_ms", C.c_float), ("main_kernel_launches", C.c_int), ("left_kernel_launches", C.c_int)]
 
 
 EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liogpu_destroy", "liogpu_last_error",
@@ -130,7 +131,9 @@ def info_to_dict(info: S2MInfo) -> dict:
                 is_degenerate=info.is_degenerate, tie_queries=info.tie_queries, delta_r=info.delta_r_deg,
                 delta_t=info.delta_t_cm, JtJ=np.array(info.JtJ).reshape(6, 6), Jtr=np.array(info.Jtr),
                 pose_hist=np.array(info.pose_hist, dtype=np.float32).reshape(LIOGPU_MAX_ITER, 6)[:it],
-                nsel_hist=np.array(info.nsel_hist)[:it], gpu_ms=info.gpu_ms)
+                nsel_hist=np.array(info.nsel_hist)[:it], gpu_ms=info.gpu_ms, seeded=info.seeded,
+                main_kernel_ms=info.main_kernel_ms, left_kernel_ms=info.left_kernel_ms,
+                main_kernel_launches=info.main_kernel_launches, left_kernel_launches=info.left_kernel_launches)
 
 
 class LioGpu:

@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
     # liogpu_params: 3 int + 2 float + 2 int + 6 float + 2 float + 6 int reserved
     assert C.sizeof(liogpu.Params) == 4 * 21
     # liogpu_s2m_info: 6 int + 2 float + 36 + 6 double + 30*6 float + 30 int + float (+ padding to 8)
-    assert C.sizeof(liogpu.S2MInfo) == 8 * 4 + 42 * 8 + 180 * 4 + 30 * 4 + 8
+    # ... + gpu_ms, seeded, 2 float kernel times, 2 int launch counts (6 x 4 bytes)
+    assert C.sizeof(liogpu.S2MInfo) == 8 * 4 + 42 * 8 + 180 * 4 + 30 * 4 + 6 * 4
 
 
 def test_defaults_follow_utility_h():
