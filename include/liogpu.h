@@ -45,6 +45,14 @@ extern "C" {
 
 typedef struct liogpu_ctx liogpu_ctx;
 
+/* Device-resident hand-off.  Passed as an OUTPUT cloud pointer to liogpu_deskew,
+ * liogpu_voxel_downsample or liogpu_downsample_scan2map it means "do not copy the result out, keep it in
+ * HBM as this context's resident cloud"; passed as an INPUT cloud pointer (n and stride are then ignored) to
+ * liogpu_voxel_downsample, liogpu_scan2map, liogpu_downsample_scan2map, liogpu_surf_optimization or
+ * liogpu_keyframe_put it means "use the resident cloud".  A co-located imageProjection + mapOptimization
+ * thus moves a sweep over PCIe once (the raw XYZIRT records) and nothing else. */
+#define LIOGPU_DEVICE_RESIDENT ((void*)(unsigned long long)1)
+
 /* Parameters the hot path reads from ParamServer (UT:199-331); defaults are UT's compiled-in ones.
  * Fill with liogpu_default_params() and override. */
 typedef struct liogpu_params {
@@ -138,6 +146,8 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s 
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);
 int liogpu_local_map_size(const liogpu_ctx* ctx);
+/* number of points of the resident cloud (0 if none) */
+int liogpu_resident_size(const liogpu_ctx* ctx);
 
 /* The loop of scan2MapOptimization (MO:1848-1859): per iteration surfOptimization (MO:1618-1687),
  * combineOptimizationCoeffs (MO:1689-1700) and LMOptimization (MO:1702-1837), entirely on device.

@@ -28,7 +28,15 @@ bool is_device_ptr(const void* p) {
 bool stride_ok(int stride) { return stride == 16 || (stride >= 32 && (stride % 4) == 0); }
 
 // caller cloud (host or device, `stride` bytes per record) -> packed float4 in dst
-int load_cloud(Ctx* c, const void* src, int n, int stride, DevBuf& dst) {
+int load_cloud(Ctx* c, const void* src, int& n, int stride, DevBuf& dst) {
+  if (src == LIOGPU_DEVICE_RESIDENT) {  // the cloud this context kept in HBM
+    if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
+    n = c->resident_n;
+    if (c->resident == &dst || n == 0) return LIOGPU_OK;
+    LIOGPU_CUDA_OK(c, dst.reserve((size_t)n * sizeof(float4)));
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst.p, c->resident->p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    return LIOGPU_OK;
+  }
   if (n < 0 || (n > 0 && !src) || !stride_ok(stride)) { c->err = "bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
   LIOGPU_CUDA_OK(c, dst.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4)));
   if (n == 0) return LIOGPU_OK;
@@ -207,7 +215,10 @@ int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
-  if (xyzi_out) {
+  if (xyzi_out == LIOGPU_DEVICE_RESIDENT) {
+    c->resident = &c->dsk_scan;
+    c->resident_n = m;
+  } else if (xyzi_out) {
     if (m > cap_out) { c->err = "liogpu_deskew: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->dsk_scan.as<float4>(), m, xyzi_out, out_stride);
     if (rc) return rc;
@@ -258,7 +269,10 @@ int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
-  if (xyzi_out) {
+  if (xyzi_out == LIOGPU_DEVICE_RESIDENT) {
+    c->resident = &c->scan_ds4;
+    c->resident_n = m;
+  } else if (xyzi_out) {
     if (m > cap_out) { c->err = "liogpu_voxel_downsample: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->scan_ds4.as<float4>(), m, xyzi_out, out_stride);
     if (rc) return rc;
@@ -364,6 +378,7 @@ int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
 }
 
 int liogpu_local_map_size(const liogpu_ctx* ctx) { return ctx ? ctx->c.n_map : 0; }
+int liogpu_resident_size(const liogpu_ctx* ctx) { return (ctx && ctx->c.resident) ? ctx->c.resident_n : 0; }
 
 static int s2m_guards(Ctx* c, int n, liogpu_s2m_info* info) {
   if (info) {
@@ -382,6 +397,7 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
   if (rc) return rc;
   Ctx* c = &ctx->c;
   if (!pose_io || !matP_io || !degenerate_io) { c->err = "liogpu_scan2map: null state pointer"; return LIOGPU_E_INVALID; }
+  if (scan_ds == LIOGPU_DEVICE_RESIDENT) n = c->resident ? c->resident_n : 0;
   rc = s2m_guards(c, n, info);
   if (rc) {
     if (info) info->is_degenerate = *degenerate_io;
@@ -407,7 +423,10 @@ int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int str
   rc = voxel_downsample_dev(c, c->scan4.as<float4>(), n, c->prm.mapping_surf_leaf_size, c->scan_ds4, &m, &overflow);
   if (rc) return rc;
   *n_ds = m;
-  if (scan_ds_out) {
+  if (scan_ds_out == LIOGPU_DEVICE_RESIDENT) {
+    c->resident = &c->scan_ds4;
+    c->resident_n = m;
+  } else if (scan_ds_out) {
     if (m > cap_out) { c->err = "liogpu_downsample_scan2map: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->scan_ds4.as<float4>(), m, scan_ds_out, out_stride);
     if (rc) return rc;
@@ -429,6 +448,7 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
   if (rc) return rc;
   Ctx* c = &ctx->c;
   if (!c->grid_valid) { c->err = "no local map installed"; return LIOGPU_E_NO_MAP; }
+  if (scan_ds == LIOGPU_DEVICE_RESIDENT) n = c->resident ? c->resident_n : 0;
   if (c->n_map <= 0 || c->grid.n_points <= 0) {  // empty map: no neighbours, nothing accepted
     for (int i = 0; i < n; ++i) {
       for (int j = 0; j < 5; ++j) {

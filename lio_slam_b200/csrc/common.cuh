@@ -120,6 +120,9 @@ struct Ctx {
   std::map<int, std::pair<DevBuf, int>> keyframes;
   // deskew
   DevBuf imu_tab, dsk_flags, dsk_scan;
+  // device-resident hand-off (LIOGPU_DEVICE_RESIDENT)
+  DevBuf* resident = nullptr;
+  int resident_n = 0;
 };
 
 #define LIOGPU_CUDA_OK(ctx, expr)                                                        \

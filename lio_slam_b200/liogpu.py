@@ -46,7 +46,9 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream"]
+           "liogpu_stream", "liogpu_resident_size"]
+
+RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
 _lib = None
 
@@ -75,6 +77,7 @@ def load_library() -> C.CDLL:
     lib.liogpu_stream.argtypes = [C.c_void_p]
     lib.liogpu_keyframe_count.argtypes = [C.c_void_p]
     lib.liogpu_local_map_size.argtypes = [C.c_void_p]
+    lib.liogpu_resident_size.argtypes = [C.c_void_p]
     lib.liogpu_keyframe_clear.argtypes = [C.c_void_p]
     lib.liogpu_deskew.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -113,6 +116,8 @@ class LioGpuError(RuntimeError):
 
 def _cloud_args(cloud):
     """-> (pointer:int, n, stride, keepalive)"""
+    if isinstance(cloud, str) and cloud == RESIDENT:
+        return 1, 0, 16, None
     if isinstance(cloud, tuple):
         ptr, n, stride = cloud
         return int(ptr), int(n), int(stride), None
@@ -174,7 +179,8 @@ class LioGpu:
     def stream(self) -> int:
         return int(self.lib.liogpu_stream(self.h) or 0)
 
-    def deskew(self, scan_xyzirt, time_scan_cur: float, imu_t, rx, ry, rz, deskew_enabled: bool = True):
+    def deskew(self, scan_xyzirt, time_scan_cur: float, imu_t, rx, ry, rz, deskew_enabled: bool = True,
+               keep_on_device: bool = False):
         ptr, n, stride, keep = _cloud_args(scan_xyzirt)
         imu_t = np.ascontiguousarray(imu_t, np.float64); rx = np.ascontiguousarray(rx, np.float64)
         ry = np.ascontiguousarray(ry, np.float64); rz = np.ascontiguousarray(rz, np.float64)
@@ -182,9 +188,14 @@ class LioGpu:
         n_out = C.c_int(0)
         st = self._check(self.lib.liogpu_deskew(self.h, ptr, n, stride, C.c_double(time_scan_cur), imu_t.ctypes.data,
                                                 rx.ctypes.data, ry.ctypes.data, rz.ctypes.data, imu_t.shape[0],
-                                                int(deskew_enabled), out.ctypes.data, 16, out.shape[0],
-                                                C.byref(n_out)))
+                                                int(deskew_enabled), 1 if keep_on_device else out.ctypes.data, 16,
+                                                out.shape[0], C.byref(n_out)))
+        if keep_on_device:
+            return n_out.value, st
         return out[: n_out.value].copy(), st
+
+    def resident_size(self) -> int:
+        return int(self.lib.liogpu_resident_size(self.h))
 
     def transform_cloud(self, cloud, pose6) -> np.ndarray:
         ptr, n, stride, keep = _cloud_args(cloud)
@@ -193,12 +204,17 @@ class LioGpu:
         self._check(self.lib.liogpu_transform_cloud(self.h, ptr, n, stride, pose.ctypes.data, out.ctypes.data, 16))
         return out
 
-    def voxel_downsample(self, cloud, leaf: float, out_stride: int = 16):
+    def voxel_downsample(self, cloud, leaf: float, out_stride: int = 16, keep_on_device: bool = False):
         ptr, n, stride, keep = _cloud_args(cloud)
+        if cloud is RESIDENT or (isinstance(cloud, str) and cloud == RESIDENT):
+            n = self.resident_size()
         out = np.empty((max(n, 1), out_stride // 4), np.float32)
         n_out = C.c_int(0)
-        st = self._check(self.lib.liogpu_voxel_downsample(self.h, ptr, n, stride, C.c_float(leaf), out.ctypes.data,
+        st = self._check(self.lib.liogpu_voxel_downsample(self.h, ptr, n, stride, C.c_float(leaf),
+                                                          1 if keep_on_device else out.ctypes.data,
                                                           out_stride, out.shape[0], C.byref(n_out)))
+        if keep_on_device:
+            return n_out.value, st
         return out[: n_out.value].copy(), st
 
     def keyframe_put(self, kid: int, cloud) -> None:
@@ -252,8 +268,11 @@ class LioGpu:
             d["is_degenerate"] = deg.value
         return pose, P.reshape(6, 6), d
 
-    def downsample_scan2map(self, scan, pose6, matP=None, degenerate: int = 0, max_iter: int = 30, fetch_ds=False):
+    def downsample_scan2map(self, scan, pose6, matP=None, degenerate: int = 0, max_iter: int = 30, fetch_ds=False,
+                            keep_ds_on_device: bool = False):
         ptr, n, stride, keep = _cloud_args(scan)
+        if isinstance(scan, str) and scan == RESIDENT:
+            n = self.resident_size()
         pose = np.array(pose6, dtype=np.float32)
         P = np.zeros(36, np.float32) if matP is None else np.array(matP, dtype=np.float32).reshape(36)
         deg = C.c_int(int(degenerate))
@@ -262,7 +281,8 @@ class LioGpu:
         out = np.empty((max(n, 1), 4), np.float32) if fetch_ds else None
         st = self._check(self.lib.liogpu_downsample_scan2map(
             self.h, ptr, n, stride, pose.ctypes.data, P.ctypes.data, C.byref(deg), max_iter, C.byref(info),
-            C.byref(n_ds), out.ctypes.data if fetch_ds else None, 16, out.shape[0] if fetch_ds else 0))
+            C.byref(n_ds), 1 if keep_ds_on_device else (out.ctypes.data if fetch_ds else None), 16,
+            out.shape[0] if fetch_ds else 0))
         d = info_to_dict(info)
         d["status"] = st
         d["is_degenerate"] = deg.value
@@ -273,6 +293,8 @@ class LioGpu:
 
     def surf_optimization(self, scan_ds, pose6=None, T12=None):
         ptr, n, stride, keep = _cloud_args(scan_ds)
+        if isinstance(scan_ds, str) and scan_ds == RESIDENT:
+            n = self.resident_size()
         idx = np.empty((n, 5), np.int32); d2 = np.empty((n, 5), np.float32)
         coeff = np.empty((n, 4), np.float32); flag = np.empty(n, np.uint8); tie = np.empty(n, np.uint8)
         pose = np.ascontiguousarray(pose6, np.float32) if pose6 is not None else None

@@ -392,3 +392,45 @@ def test_replay_driver_tracks_ground_truth(world, tmp_path):
     assert np.abs(poses[:, 3:] - gts[:, 3:]).max() < 0.08 and np.abs(poses[:, :3] - gts[:, :3]).max() < 0.01
     assert (rows[1:, 7] >= 1).all() and (rows[1:, 8] > 500).all()
     print(summary)
+
+
+def test_device_resident_pipeline_config2(oracle, world):
+    # BASELINE configs[1]: 32-beam sweep with 200 Hz IMU deskew + scan-to-map, the sweep crossing PCIe once:
+    # deskew (kept in HBM) -> VoxelGrid + registration on the resident cloud -> keyframe from the resident
+    # downsampled sweep.  Every stage must equal the oracle pipeline run stage by stage on the host.
+    from lio_slam_b200.liogpu import LioGpu, RESIDENT
+    from oracle.oracle import DeskewParams
+    kw = dict(n_scan=32, downsample_rate=1, point_filter_num=1, lidar_min_front=2.0, lidar_min_back=10.0,
+              lidar_min_left=2.0, lidar_min_right=2.0, lidar_max_range=100.0, lidar_max_intensity=100.0,
+              mapping_surf_leaf_size=0.4, surrounding_keyframe_map_leaf_size=0.5)
+    g = LioGpu(**kw)
+    try:
+        pose_gt = synth.path_pose(0.5)
+        scan = synth.make_scan(world, pose_gt, 32, seed=91, cols=900)
+        t0 = 1700000100.0
+        imu_t, rx, ry, rz = synth.make_imu_table(t0, seed=12)
+        map4 = synth.make_local_map(world, 32, 30000, 0.5, seed=6, s0=0.0, cols=900, max_poses=32)
+        guess = synth.perturbed_guess(pose_gt, 33)
+        dp = DeskewParams(32, 1, 1, 2.0, 10.0, 2.0, 2.0, 100.0, 100.0)
+        dsk = oracle.deskew(scan, dp, t0, imu_t, rx, ry, rz, True)
+        ds, _ = oracle.voxel_grid(dsk, 0.4)
+        ref_pose, ref_P, ref_info = oracle.scan2map(map4, ds, guess, threads=8)
+        g.set_local_map(map4)
+        n_dsk, st = g.deskew(scan, t0, imu_t, rx, ry, rz, True, keep_on_device=True)
+        assert n_dsk == dsk.shape[0] == g.resident_size()
+        pose, P, info = g.downsample_scan2map(RESIDENT, guess, keep_ds_on_device=True)
+        assert info["n_ds"] == ds.shape[0] == g.resident_size()
+        check_s2m(pose, info, ref_pose, ref_info)
+        # the resident downsampled sweep becomes a keyframe without leaving the GPU; rebuilding the local
+        # map from it must equal the oracle's extractCloud on the same cloud and pose
+        g.keyframe_clear()
+        g.keyframe_put(0, RESIDENT)
+        got, _ = g.build_local_map([0], pose.reshape(1, 6), 0.5)
+        want, _ = oracle.build_local_map([ds], pose.reshape(1, 6), 0.5)
+        assert_biteq(got, want, "keyframe from resident cloud")
+        # and the resident cloud can be voxelised / inspected again
+        again, _ = g.voxel_downsample(RESIDENT, 0.8)
+        want2, _ = oracle.voxel_grid(ds, 0.8)
+        assert_biteq(again, want2)
+    finally:
+        g.close()
