@@ -134,7 +134,7 @@ int liogpu_create(liogpu_ctx** out, const liogpu_params* params) {
       cudaEventCreateWithFlags(&c.ev_it0, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess ||
-      cudaHostAlloc(&c.h_pinned, 131072, cudaHostAllocDefault) != cudaSuccess) {
+      cudaHostAlloc(&c.h_pinned, 262144, cudaHostAllocDefault) != cudaSuccess) {
     liogpu_destroy(ctx);
     return LIOGPU_E_CUDA;
   }
@@ -329,19 +329,27 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
     c->err = "too many keyframes in one local map (max 1365)";
     return LIOGPU_E_INVALID;
   }
-  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve((size_t)k * 6 * sizeof(float) + 64));  // pose table (scratch)
-  float* hposes = reinterpret_cast<float*>((char*)c->h_pinned + 8192);
+  // staging (pinned, second half of h_pinned): poses [k*6 f32] | offsets [k+1 i32] | source pointers [k u64]
+  char* hp = (char*)c->h_pinned + 131072;
+  float* hposes = reinterpret_cast<float*>(hp);
+  int* hoffs = reinterpret_cast<int*>(hp + 32768);
+  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
   std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
-  float* d_poses = c->dbg_d2.as<float>();
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d_poses, hposes, (size_t)k * 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   size_t off = 0;
-  for (int f = 0; f < k; ++f) {  // transformPointCloud + "+=" concatenation (mapOptmization.cpp:1566-1576)
+  for (int f = 0; f < k; ++f) {  // transformPointCloud + "+=" concatenation order (mapOptmization.cpp:1566-1576)
     auto& kf = c->keyframes[ids[f]];
-    LIOGPU_CUDA_OK(c, launch_transform(c, kf.first.as<float4>(), kf.second, d_poses + 6 * f,
-                                       c->map_raw4.as<float4>() + off));
+    hoffs[f] = (int)off;
+    hsrcs[f] = kf.first.as<float4>();
     off += (size_t)kf.second;
   }
+  hoffs[k] = (int)off;
+  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));  // scratch: tables + k transforms
+  char* dp = (char*)c->dbg_d2.p;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  LIOGPU_CUDA_OK(c, launch_transform_multi(c, reinterpret_cast<const float4* const*>(dp + 49152),
+                                           reinterpret_cast<const int*>(dp + 32768), k, reinterpret_cast<const float*>(dp),
+                                           reinterpret_cast<float*>(dp + 65536), (long long)total, c->map_raw4.as<float4>()));
   int m = 0;
   bool overflow = false;
   rc = voxel_downsample_dev(c, c->map_raw4.as<float4>(), (int)total, leaf, c->map4, &m, &overflow);

@@ -46,6 +46,7 @@ struct VoxelSetup {
   unsigned n_cells;   // div.x*div.y*div.z (valid when !overflow)
   int n_valid;        // finite points
   int key_bits;       // bits needed to sort keys in [0, n_cells]
+  unsigned n_vox;     // number of occupied voxels (written by the last stage)
 };
 
 // ---- sorted-grid 5-NN index over the local map ----
@@ -139,8 +140,11 @@ struct Ctx {
 cudaError_t launch_unpack(Ctx* c, const void* d_raw, int n, int stride, float4* out);
 cudaError_t launch_pack(Ctx* c, const float4* in, int n, void* d_raw, int stride);
 cudaError_t launch_transform(Ctx* c, const float4* in, int n, const float* d_pose6, float4* out);
+cudaError_t launch_transform_multi(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
+                                   float* d_T12, long long total, float4* out);
 // --- sort.cu
-cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, uint32_t** keys_out, uint32_t** vals_out);
+cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, const int* d_key_bits, uint32_t** keys_out,
+                             uint32_t** vals_out);
 cudaError_t exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, int n, uint32_t* d_total);
 // --- voxel.cu
 cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm);

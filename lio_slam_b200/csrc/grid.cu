@@ -132,7 +132,7 @@ int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
   int bits = 0;
   while (bits < 32 && (g.n_cells >> bits) != 0u) ++bits;
   uint32_t *skeys = nullptr, *sperm = nullptr;
-  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, bits, &skeys, &sperm));
+  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, bits, nullptr, &skeys, &sperm));
   grid_gather_kernel<<<div_up(g.n_points, 256), 256, 0, c->stream>>>(map4, sperm, g.n_points,
                                                                       c->map_sorted.as<float4>());
   c->launches++;

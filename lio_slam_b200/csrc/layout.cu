@@ -55,6 +55,42 @@ __global__ void transform_kernel(const float4* __restrict__ in, int n, const flo
   out[i] = apply_T(T, in[i]);
 }
 
+// extractCloud (mapOptmization.cpp:1556-1588): all keyframes of a local map in ONE launch instead of one
+// transformPointCloud per keyframe.  pose_table_kernel builds the k 3x4 transforms; transform_multi_kernel
+// finds the keyframe of every output point by binary search in the offset table (k <= 1365, L1-resident).
+__global__ void pose_table_kernel(const float* __restrict__ poses6, int k, float* __restrict__ T12) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= k) return;
+  float T[12];
+  pose_to_T(poses6 + 6 * f, T);
+#pragma unroll
+  for (int q = 0; q < 12; ++q) T12[12 * f + q] = T[q];
+}
+__global__ void __launch_bounds__(256)
+transform_multi_kernel(const float4* const* __restrict__ srcs, const int* __restrict__ offs, int k,
+                       const float* __restrict__ T12, long long total, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = k;  // offs[lo] <= i < offs[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(offs + mid) <= i) lo = mid; else hi = mid;
+  }
+  const float4 p = srcs[lo][i - __ldg(offs + lo)];
+  float T[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) T[q] = __ldg(T12 + 12 * lo + q);
+  out[i] = apply_T(T, p);
+}
+cudaError_t launch_transform_multi(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
+                                   float* d_T12, long long total, float4* out) {
+  if (k <= 0 || total <= 0) return cudaSuccess;
+  pose_table_kernel<<<div_up(k, 128), 128, 0, c->stream>>>(d_poses6, k, d_T12);
+  transform_multi_kernel<<<div_up(total, 256), 256, 0, c->stream>>>(d_srcs, d_offs, k, d_T12, total, out);
+  c->launches += 2;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(Ctx* c, const void* d_raw, int n, int stride, float4* out) {
   if (n <= 0) return cudaSuccess;
   unpack_kernel<<<div_up(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_raw, n, stride, out);

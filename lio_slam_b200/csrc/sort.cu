@@ -21,8 +21,9 @@ constexpr int RS_MAX_BLOCKS = 1024;
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int tiles_per_block,
-               uint32_t* __restrict__ counters, int nblocks) {
+               uint32_t* __restrict__ counters, int nblocks, const int* __restrict__ d_key_bits) {
   __shared__ uint32_t hist[256];
+  if (d_key_bits && shift >= *d_key_bits) return;  // pass not needed for this key range
   hist[threadIdx.x] = 0;
   __syncthreads();
   const long long begin = (long long)blockIdx.x * tiles_per_block * RS_TILE;
@@ -36,8 +37,10 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, int tiles_pe
 
 // One CTA per digit: exclusive scan of that digit's per-block counts (nblocks <= 1024).
 __global__ void __launch_bounds__(1024)
-rs_scan_kernel(uint32_t* __restrict__ counters, int nblocks, uint32_t* __restrict__ digit_total) {
+rs_scan_kernel(uint32_t* __restrict__ counters, int nblocks, uint32_t* __restrict__ digit_total, int shift,
+               const int* __restrict__ d_key_bits) {
   __shared__ uint32_t warp_sum[32];
+  if (d_key_bits && shift >= *d_key_bits) return;
   const int d = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
   uint32_t v = t < nblocks ? counters[(size_t)d * nblocks + t] : 0u;
   uint32_t x = v;
@@ -67,8 +70,19 @@ __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,  // vals_in may be null: iota
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
                   int tiles_per_block, const uint32_t* __restrict__ counters, int nblocks,
-                  const uint32_t* __restrict__ digit_total) {
+                  const uint32_t* __restrict__ digit_total, const int* __restrict__ d_key_bits) {
   __shared__ uint32_t warp_hist[RS_WARPS][256];
+  if (d_key_bits && shift >= *d_key_bits) {
+    // every remaining digit is zero: the pass would be the identity permutation — just move the data
+    const long long begin0 = (long long)blockIdx.x * tiles_per_block * RS_TILE;
+    long long end0 = begin0 + (long long)tiles_per_block * RS_TILE;
+    if (end0 > n) end0 = n;
+    for (long long i = begin0 + threadIdx.x; i < end0; i += RS_THREADS) {
+      keys_out[i] = keys_in[i];
+      vals_out[i] = vals_in ? vals_in[i] : (uint32_t)i;
+    }
+    return;
+  }
   __shared__ uint32_t running[256];
   __shared__ uint32_t wsum[RS_WARPS];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -146,10 +160,15 @@ __global__ void iota_kernel(uint32_t* v, int n) {
 
 // Sort the n pairs whose keys are in c->keys0 (values implicit iota on the first pass).  On return
 // *keys_out / *vals_out point at whichever ping-pong buffer holds the result.
-cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, uint32_t** keys_out, uint32_t** vals_out) {
+// key_bits >= 0: the host knows the key width and runs ceil(key_bits/8) passes.
+// key_bits <  0: the width is only known on the device (*d_key_bits); four passes are enqueued and the ones
+//                beyond the width degrade to a copy, so no host round trip is needed.
+cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, const int* d_key_bits, uint32_t** keys_out,
+                             uint32_t** vals_out) {
   uint32_t* k[2] = {c->keys0.as<uint32_t>(), c->keys1.as<uint32_t>()};
   uint32_t* v[2] = {c->vals0.as<uint32_t>(), c->vals1.as<uint32_t>()};
-  const int passes = (key_bits + 7) / 8;
+  const int passes = key_bits >= 0 ? (key_bits + 7) / 8 : 4;
+  if (key_bits >= 0) d_key_bits = nullptr;
   int cur = 0;
   if (n <= 0) { *keys_out = k[0]; *vals_out = v[0]; return cudaSuccess; }
   if (passes == 0) {
@@ -168,10 +187,10 @@ cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, uint32_t** keys_out, u
   uint32_t* digit_total = counters + (size_t)256 * nb;
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
-    rs_hist_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], n, shift, tiles_per_block, counters, nb);
-    rs_scan_kernel<<<256, 1024, 0, c->stream>>>(counters, nb, digit_total);
+    rs_hist_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], n, shift, tiles_per_block, counters, nb, d_key_bits);
+    rs_scan_kernel<<<256, 1024, 0, c->stream>>>(counters, nb, digit_total, shift, d_key_bits);
     rs_scatter_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], p == 0 ? nullptr : v[cur], k[cur ^ 1], v[cur ^ 1], n,
-                                                        shift, tiles_per_block, counters, nb, digit_total);
+                                                        shift, tiles_per_block, counters, nb, digit_total, d_key_bits);
     c->launches += 3;
     cur ^= 1;
   }

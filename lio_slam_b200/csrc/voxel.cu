@@ -127,39 +127,122 @@ vox_key_kernel(const float4* __restrict__ pts, int n, const VoxelSetup* __restri
   keys[i] = key;
 }
 
+// head[i] = 1 at the first sorted position of every occupied voxel (finite points only), else 0
 __global__ void __launch_bounds__(256)
-vox_head_kernel(const uint32_t* __restrict__ keys, int n_valid, uint32_t* __restrict__ head) {
+vox_head_kernel(const uint32_t* __restrict__ keys, int n, const VoxelSetup* __restrict__ sp, uint32_t* __restrict__ head) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
-  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  if (i >= n) return;
+  const int n_valid = sp->overflow ? 0 : sp->n_valid;
+  head[i] = (i < n_valid && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;
 }
 
 // seg_start[v] = first sorted position of voxel v; seg_start[n_vox] = n_valid
 __global__ void __launch_bounds__(256)
-vox_segstart_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, int n_valid,
-                    uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ n_vox) {
+vox_segstart_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, int n,
+                    VoxelSetup* __restrict__ sp, uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ n_vox) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) seg_start[*n_vox] = (uint32_t)n_valid;
+  const int n_valid = sp->overflow ? 0 : sp->n_valid;
+  if (i == 0) { seg_start[*n_vox] = (uint32_t)n_valid; sp->n_vox = *n_vox; }
   if (i >= n_valid) return;
   if (i == 0 || keys[i] != keys[i - 1]) seg_start[rank[i]] = (uint32_t)i;
 }
 
-// One thread per voxel: sequential f32 sums in ascending input index (the sort is stable), true
-// division by (float)n — bit-identical to the canonical VoxelGrid (A.1 step 7).
+// Per-voxel centroid: SEQUENTIAL f32 sums in ascending input index (the sort is stable), true division by
+// (float)n — bit-identical to the canonical VoxelGrid (A.1 step 7).  The additions of one voxel cannot be
+// reordered, but the LOADS can.
+//   vox_centroid_kernel       one thread per voxel; a voxel with <= 8 members is finished here (all member
+//                             loads issued before the adds); a longer one is appended to `long_list`.
+//   vox_centroid_long_kernel  persistent warps, one long voxel at a time (dynamic: the sizes are heavy
+//                             tailed — thousands of members near the sensor when 50 keyframes overlap): the
+//                             warp gathers 128 members per step (next step prefetched), stages them in
+//                             shared memory, and four lanes — one per component x, y, z, intensity — run the
+//                             sequential sums from there (~5 cycles per member instead of one L2 round trip).
+constexpr unsigned VOX_SHORT = 8;
+constexpr int VOX_LONG_K = 4;                    // 32-member loads per lane and step
+constexpr int VOX_LONG_CHUNK = 32 * VOX_LONG_K;  // 128 members per step
+constexpr int VOX_LONG_WARPS = 4;
+
 __global__ void __launch_bounds__(256)
 vox_centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ perm,
                     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ n_vox_p,
-                    float4* __restrict__ out) {
+                    float4* __restrict__ out, uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
+  const unsigned nv = *n_vox_p;
   const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= *n_vox_p) return;
-  const uint32_t s = seg_start[v], e = seg_start[v + 1];
-  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  for (uint32_t j = s; j < e; ++j) {
-    const float4 p = pts[perm[j]];
-    sx += p.x; sy += p.y; sz += p.z; si += p.w;
+  const unsigned lane = threadIdx.x & 31;
+  if ((v & ~31u) >= nv) return;  // whole warp beyond the last voxel
+  uint32_t s = 0, e = 0;
+  if (v < nv) { s = seg_start[v]; e = seg_start[v + 1]; }
+  const uint32_t cnt = e - s;
+  const bool is_long = v < nv && cnt > VOX_SHORT;
+  if (v < nv && !is_long) {
+    float4 p[VOX_SHORT];
+#pragma unroll
+    for (unsigned k = 0; k < VOX_SHORT; ++k) p[k] = pts[perm[s + (k < cnt ? k : 0)]];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+#pragma unroll
+    for (unsigned k = 0; k < VOX_SHORT; ++k)
+      if (k < cnt) { sx += p[k].x; sy += p[k].y; sz += p[k].z; si += p[k].w; }
+    const float c = (float)cnt;
+    out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
   }
-  const float cnt = (float)(e - s);
-  out[v] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+  const unsigned lm = __ballot_sync(0xffffffffu, is_long);
+  if (lm) {  // one atomic per warp reserves slots for its long voxels (order in the list is irrelevant)
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(long_count, (uint32_t)__popc(lm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (is_long) long_list[base + __popc(lm & ((1u << lane) - 1u))] = v;
+  }
+}
+
+__global__ void __launch_bounds__(32 * VOX_LONG_WARPS)
+vox_centroid_long_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ perm,
+                         const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ long_list,
+                         const uint32_t* __restrict__ long_count, uint32_t* __restrict__ work_counter,
+                         float4* __restrict__ out) {
+  __shared__ float4 stage[VOX_LONG_WARPS][VOX_LONG_CHUNK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t total = *long_count;
+  float4* st = stage[warp];
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    const uint32_t v = long_list[item];
+    const uint32_t s = seg_start[v], e = seg_start[v + 1];
+    float4 cur[VOX_LONG_K], nxt[VOX_LONG_K];
+#pragma unroll
+    for (int k = 0; k < VOX_LONG_K; ++k) {
+      const uint32_t j = s + k * 32 + lane;
+      cur[k] = j < e ? pts[perm[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float acc = 0.f;  // lane c < 4 accumulates component c
+    for (uint32_t base = s; base < e; base += VOX_LONG_CHUNK) {
+      const uint32_t nb = base + VOX_LONG_CHUNK;
+#pragma unroll
+      for (int k = 0; k < VOX_LONG_K; ++k) {  // prefetch the next step while this one is consumed
+        const uint32_t j = nb + k * 32 + lane;
+        nxt[k] = j < e ? pts[perm[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < VOX_LONG_K; ++k) st[k * 32 + lane] = cur[k];
+      __syncwarp();
+      if (lane < 4) {
+        const int m = (int)min((uint32_t)VOX_LONG_CHUNK, e - base);
+        const float* f = reinterpret_cast<const float*>(st) + lane;
+#pragma unroll 8
+        for (int i = 0; i < m; ++i) acc += f[4 * i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < VOX_LONG_K; ++k) cur[k] = nxt[k];
+    }
+    const float c = (float)(e - s);
+    const float r = acc / c;
+    const float rx = __shfl_sync(0xffffffffu, r, 0), ry = __shfl_sync(0xffffffffu, r, 1);
+    const float rz = __shfl_sync(0xffffffffu, r, 2), ri = __shfl_sync(0xffffffffu, r, 3);
+    if (lane == 0) out[v] = make_float4(rx, ry, rz, ri);
+  }
 }
 
 // f32 min/max + finite count of a cloud into mm[7] (ordered-uint encoding); shared with grid.cu
@@ -174,8 +257,10 @@ cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm) {
   return cudaGetLastError();
 }
 
-// Device-resident VoxelGrid: in (n float4) -> out (n_out float4).  One small D2H sync for the setup
-// block (the host must size the sort) and one for the voxel count.
+// Device-resident VoxelGrid: in (n float4) -> out (n_out float4).  Everything is enqueued without waiting
+// for the host: the key width, the finite count and the overflow flag stay on the device (the radix sort
+// runs a fixed four passes, the unneeded ones degrade to a copy); ONE read-back at the end returns the voxel
+// count and the guard flag.
 int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& out, int* n_out, bool* overflow) {
   *n_out = 0;
   *overflow = false;
@@ -190,44 +275,41 @@ int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& ou
   LIOGPU_CUDA_OK(c, c->seg_flag.reserve((size_t)n * 4 + 16));
   LIOGPU_CUDA_OK(c, c->seg_start.reserve((size_t)n * 4 + 16));
   LIOGPU_CUDA_OK(c, c->misc.reserve(256));
+  LIOGPU_CUDA_OK(c, out.reserve((size_t)n * sizeof(float4)));
   unsigned* mm = c->minmax.as<unsigned>();
   VoxelSetup* d_setup = c->vox_setup.as<VoxelSetup>();
   LIOGPU_CUDA_OK(c, launch_minmax(c, in, n, mm));
   vox_setup_kernel<<<1, 32, 0, c->stream>>>(mm, leaf, d_setup);
-  c->launches += 1;
+  vox_key_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(in, n, d_setup, c->keys0.as<uint32_t>());
+  c->launches += 2;
+  uint32_t *skeys = nullptr, *sperm = nullptr;
+  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, -1, &d_setup->key_bits, &skeys, &sperm));
+  uint32_t* head = c->seg_flag.as<uint32_t>();
+  uint32_t* d_nvox = c->misc.as<uint32_t>();
+  vox_head_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(skeys, n, d_setup, head);
+  c->launches++;
+  LIOGPU_CUDA_OK(c, exclusive_scan_u32(c, head, head, n, d_nvox));
+  vox_segstart_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(skeys, head, n, d_setup, c->seg_start.as<uint32_t>(), d_nvox);
+  // long-voxel list: reuses the (now dead) unsorted-key ping-pong buffer; two counters in misc
+  uint32_t* long_list = (skeys == c->keys0.as<uint32_t>()) ? c->keys1.as<uint32_t>() : c->keys0.as<uint32_t>();
+  uint32_t* d_long = c->misc.as<uint32_t>() + 2;  // [0] long count, [1] work counter
+  LIOGPU_CUDA_OK(c, cudaMemsetAsync(d_long, 0, 2 * sizeof(uint32_t), c->stream));
+  vox_centroid_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(in, sperm, c->seg_start.as<uint32_t>(), d_nvox,
+                                                             out.as<float4>(), long_list, d_long);
+  vox_centroid_long_kernel<<<c->sm_count * 8, 32 * VOX_LONG_WARPS, 0, c->stream>>>(
+      in, sperm, c->seg_start.as<uint32_t>(), long_list, d_long, d_long + 1, out.as<float4>());
+  c->launches += 3;
+  LIOGPU_CUDA_OK(c, cudaGetLastError());
   VoxelSetup* h_setup = reinterpret_cast<VoxelSetup*>(c->h_pinned);
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_setup, d_setup, sizeof(VoxelSetup), cudaMemcpyDeviceToHost, c->stream));
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  const VoxelSetup hs = *h_setup;
-  if (hs.overflow) {  // q4: PCL warns and returns the input unchanged
-    LIOGPU_CUDA_OK(c, out.reserve((size_t)n * sizeof(float4)));
+  if (h_setup->overflow) {  // q4: PCL warns and returns the input unchanged
     LIOGPU_CUDA_OK(c, cudaMemcpyAsync(out.p, in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
     *n_out = n;
     *overflow = true;
     return LIOGPU_OK;
   }
-  if (hs.n_valid <= 0) return LIOGPU_OK;
-  vox_key_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(in, n, d_setup, c->keys0.as<uint32_t>());
-  c->launches++;
-  uint32_t *skeys = nullptr, *sperm = nullptr;
-  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, hs.key_bits, &skeys, &sperm));
-  uint32_t* head = c->seg_flag.as<uint32_t>();
-  uint32_t* d_nvox = c->misc.as<uint32_t>();
-  vox_head_kernel<<<div_up(hs.n_valid, 256), 256, 0, c->stream>>>(skeys, hs.n_valid, head);
-  c->launches++;
-  LIOGPU_CUDA_OK(c, exclusive_scan_u32(c, head, head, hs.n_valid, d_nvox));
-  vox_segstart_kernel<<<div_up(hs.n_valid, 256), 256, 0, c->stream>>>(skeys, head, hs.n_valid,
-                                                                       c->seg_start.as<uint32_t>(), d_nvox);
-  c->launches++;
-  // upper bound of the voxel count is n_valid: launch for that and let surplus threads exit
-  LIOGPU_CUDA_OK(c, out.reserve((size_t)hs.n_valid * sizeof(float4)));
-  vox_centroid_kernel<<<div_up(hs.n_valid, 256), 256, 0, c->stream>>>(in, sperm, c->seg_start.as<uint32_t>(), d_nvox,
-                                                                      out.as<float4>());
-  c->launches++;
-  uint32_t* h_nvox = reinterpret_cast<uint32_t*>((char*)c->h_pinned + 1024);
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_nvox, d_nvox, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  *n_out = (int)*h_nvox;
+  *n_out = (int)h_setup->n_vox;
   return LIOGPU_OK;
 }
 
