@@ -325,8 +325,16 @@ def main():
     else:
         dom, launch_us = "s2m_left_kernel", 1e3 * kern["left_ms"] / max(kern["left_n"], 1)
     achieved = 96.0 * nq / (launch_us * 1e-6) / 1e9
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same workload only)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom)
+        if tr and tr.get("n_query") == nq and tr.get("workload") == name:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 96 * nq, "avg_launch_us": launch_us,
                 "main_kernel_us": 1e3 * kern["main_ms"] / max(kern["main_n"], 1),
                 "left_kernel_us": 1e3 * kern["left_ms"] / max(kern["left_n"], 1),

@@ -27,7 +27,7 @@ namespace liogpu {
 #define S2M_THREADS_CFG 256
 #endif
 #ifndef S2M_MINBLOCKS_CFG
-#define S2M_MINBLOCKS_CFG 3
+#define S2M_MINBLOCKS_CFG 4
 #endif
 constexpr int S2M_THREADS = S2M_THREADS_CFG;
 constexpr int S2M_SUMS = 32;  // 21 (upper AtA) + 6 (AtB) + nsel + ties, padded to 32
