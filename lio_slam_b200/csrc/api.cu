@@ -405,7 +405,10 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
   if (rc) return rc;
   Ctx* c = &ctx->c;
   if (!pose_io || !matP_io || !degenerate_io) { c->err = "liogpu_scan2map: null state pointer"; return LIOGPU_E_INVALID; }
-  if (scan_ds == LIOGPU_DEVICE_RESIDENT) n = c->resident ? c->resident_n : 0;
+  if (scan_ds == LIOGPU_DEVICE_RESIDENT) {
+    if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
+    n = c->resident_n;
+  }
   rc = s2m_guards(c, n, info);
   if (rc) {
     if (info) info->is_degenerate = *degenerate_io;
@@ -456,7 +459,10 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
   if (rc) return rc;
   Ctx* c = &ctx->c;
   if (!c->grid_valid) { c->err = "no local map installed"; return LIOGPU_E_NO_MAP; }
-  if (scan_ds == LIOGPU_DEVICE_RESIDENT) n = c->resident ? c->resident_n : 0;
+  if (scan_ds == LIOGPU_DEVICE_RESIDENT) {
+    if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
+    n = c->resident_n;
+  }
   if (c->n_map <= 0 || c->grid.n_points <= 0) {  // empty map: no neighbours, nothing accepted
     for (int i = 0; i < n; ++i) {
       for (int j = 0; j < 5; ++j) {

@@ -1,0 +1,207 @@
+"""GPU edge cases and randomized property checks (through the C ABI, against the oracle): tiny and empty maps,
+duplicate points and exact ties, coincident query/map points, huge sparse extents (grid cell doubling), voxel
+boundary values, deskew corner cases, repeated use of one context."""
+import numpy as np
+import pytest
+
+from lio_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+I12 = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+
+
+def biteq(a, b):
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def compare_surf(gpu, oracle, map4, q4, T=I12, threads=8):
+    ref = oracle.surf_optimization(map4, q4, T12=T, threads=threads)
+    gpu.set_local_map(map4)
+    got = gpu.surf_optimization(q4, T12=T)
+    gate = ref["nn_d2"][:, 4] < 1.0
+    assert np.array_equal(got["nn_idx"][gate], ref["nn_idx"][gate])
+    assert biteq(got["nn_d2"][gate], ref["nn_d2"][gate])
+    assert np.array_equal(got["tie"][gate], ref["tie"][gate])
+    assert (got["nn_d2"][~gate, 4] >= 1.0).all()
+    assert np.array_equal(got["flag"], ref["flag"])
+    assert biteq(got["coeff"], ref["coeff"])
+    return ref, gate
+
+
+@pytest.mark.parametrize("nm", [0, 1, 4, 5, 6, 17])
+def test_tiny_maps(gpu, oracle, nm):
+    rng = np.random.default_rng(nm)
+    map4 = (rng.normal(0, 0.2, (nm, 4)) + [3, 1, 0, 0]).astype(np.float32)
+    q = (rng.normal(0, 0.3, (200, 4)) + [3, 1, 0, 0]).astype(np.float32)
+    if nm < 5:   # fewer than 5 map points: no correspondences at all
+        gpu.set_local_map(map4)
+        got = gpu.surf_optimization(q, T12=I12)
+        assert not got["flag"].any() and (got["nn_idx"] == -1).all()
+    else:
+        compare_surf(gpu, oracle, map4, q)
+
+
+def test_duplicates_and_coincident_points(gpu, oracle):
+    rng = np.random.default_rng(11)
+    base = rng.uniform(-4, 4, (3000, 4)).astype(np.float32)
+    base[:, 2] *= 0.05
+    map4 = np.concatenate([base, base[:1500], base[:700]])          # exact duplicates -> equidistant ties
+    map4 = map4[rng.permutation(map4.shape[0])]
+    q = np.concatenate([base[:2000], rng.uniform(-4, 4, (2000, 4)).astype(np.float32)])   # queries ON map points (d = 0)
+    q[2000:, 2] *= 0.05
+    ref, gate = compare_surf(gpu, oracle, map4, q)
+    assert ref["tie"].sum() > 500 and (ref["nn_d2"][:2000, 0] == 0).all()
+
+
+def test_huge_sparse_extent_forces_cell_doubling(gpu, oracle):
+    # clusters spread over 6 km x 6 km x 400 m: a 0.4 m grid would need 5e10 cells, so the cell edge doubles
+    # until the table fits; results must not change
+    rng = np.random.default_rng(5)
+    centres = np.column_stack([rng.uniform(-3000, 3000, 40), rng.uniform(-3000, 3000, 40), rng.uniform(-200, 200, 40)])
+    pts = []
+    for c in centres:
+        p = rng.normal(0, 1.0, (400, 3)); p[:, 2] *= 0.02
+        pts.append(p + c)
+    map4 = np.column_stack([np.concatenate(pts), np.zeros(16000)]).astype(np.float32)
+    q = map4[rng.choice(16000, 3000, replace=False)].copy()
+    q[:, :3] += rng.normal(0, 0.05, (3000, 3)).astype(np.float32)
+    ref, gate = compare_surf(gpu, oracle, map4, q)
+    assert gate.sum() > 2000
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_planar_scenes(gpu, oracle, seed):
+    rng = np.random.default_rng(100 + seed)
+    n_planes = rng.integers(1, 6)
+    pts = []
+    for _ in range(n_planes):
+        R = synth.rpy_to_R(*rng.uniform(-1.5, 1.5, 3))
+        p = np.column_stack([rng.uniform(-6, 6, 4000), rng.uniform(-6, 6, 4000), rng.normal(0, 0.01, 4000)])
+        pts.append(p @ R.T + rng.uniform(-3, 3, 3))
+    allp = np.concatenate(pts)
+    leaf = float(rng.choice([0.15, 0.2, 0.3, 0.5]))
+    map4, _ = oracle.voxel_grid(np.column_stack([allp, np.zeros(allp.shape[0])]).astype(np.float32), leaf)
+    got, _ = gpu.voxel_downsample(np.column_stack([allp, np.zeros(allp.shape[0])]).astype(np.float32), leaf)
+    assert biteq(got, map4)
+    q = allp[rng.choice(allp.shape[0], 3000, replace=False)] + rng.normal(0, 0.03, (3000, 3))
+    q4 = np.column_stack([q, np.ones(3000)]).astype(np.float32)
+    pose = np.concatenate([rng.uniform(-0.02, 0.02, 3), rng.uniform(-0.05, 0.05, 3)]).astype(np.float32)
+    T = oracle.pose_to_T(pose)
+    compare_surf(gpu, oracle, map4, q4, T)
+    # and the full loop from that pose
+    ref_pose, ref_P, ref_info = oracle.scan2map(map4, q4, pose, threads=8)
+    pose_g, P_g, info = gpu.scan2map(q4, pose)
+    assert info["iterations"] == ref_info["iterations"] and np.array_equal(info["nsel_hist"], ref_info["nsel_hist"])
+    assert np.abs(pose_g[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose_g[3:] - ref_pose[3:]).max() <= 1e-4
+    assert info["is_degenerate"] == ref_info["is_degenerate"]
+    assert np.abs(P_g - ref_P).max() <= 1e-5
+
+
+def test_voxel_boundary_values(gpu, oracle):
+    # coordinates exactly on voxel faces, negative zero, negative coordinates, leaf not representable in binary
+    g = np.arange(-8, 8.01, 0.5, dtype=np.float32)
+    X, Y, Z = np.meshgrid(g, g, np.array([-0.5, -0.0, 0.0, 0.3], np.float32), indexing="ij")
+    cloud = np.column_stack([X.ravel(), Y.ravel(), Z.ravel(), np.arange(X.size) % 97]).astype(np.float32)
+    cloud = np.concatenate([cloud, cloud[::3] + np.float32(1e-7)])
+    for leaf in (0.5, 0.3, 0.25, 1.0, 0.1):
+        want, ov = oracle.voxel_grid(cloud, leaf)
+        got, st = gpu.voxel_downsample(cloud, leaf)
+        assert biteq(got, want), leaf
+
+
+def test_voxel_heavy_voxels(gpu, oracle):
+    # a few voxels with tens of thousands of members (the warp-per-voxel path) next to many singletons
+    rng = np.random.default_rng(8)
+    heavy = np.concatenate([rng.normal(c, 0.03, (40000, 3)) for c in ([0.25, 0.25, 0.25], [5.25, -3.25, 1.25], [-7.75, 2.25, 0.25])])
+    light = rng.uniform(-20, 20, (60000, 3))
+    xyz = np.concatenate([heavy, light])[rng.permutation(180000)]
+    cloud = np.column_stack([xyz, rng.uniform(0, 255, 180000)]).astype(np.float32)
+    want, _ = oracle.voxel_grid(cloud, 0.5)
+    got, _ = gpu.voxel_downsample(cloud, 0.5)
+    assert biteq(got, want)
+
+
+def test_deskew_corner_cases(oracle, world):
+    from lio_slam_b200.liogpu import LioGpu
+    from oracle.oracle import DeskewParams
+    scan = synth.make_scan(world, synth.path_pose(2.0), 16, seed=5, cols=200)
+    t0 = 50.0
+    imu_t, rx, ry, rz = synth.make_imu_table(t0, seed=2)
+    base = dict(n_scan=16, downsample_rate=1, point_filter_num=1, lidar_min_front=1.0, lidar_min_back=5.0, lidar_min_left=2.0,
+                lidar_min_right=2.0, lidar_max_range=1000.0, lidar_max_intensity=100.0)
+
+    def run(kw, imu, enabled=True, sc=scan, t_scan=t0):
+        g = LioGpu(**kw)
+        try:
+            dp = DeskewParams(kw["n_scan"], kw["downsample_rate"], kw["point_filter_num"], kw["lidar_min_front"], kw["lidar_min_back"],
+                              kw["lidar_min_left"], kw["lidar_min_right"], kw["lidar_max_range"], kw["lidar_max_intensity"])
+            want = oracle.deskew(sc, dp, t_scan, *imu, enabled)
+            got, st = g.deskew(sc, t_scan, *imu, enabled)
+            assert got.shape == want.shape
+            if want.shape[0]:
+                assert np.abs(got - want).max() <= 1e-5
+            return want.shape[0]
+        finally:
+            g.close()
+    assert run(base, (imu_t, rx, ry, rz)) > 0
+    # a single IMU row: imuAvailable is false in the reference (IP:413) -> points pass through unchanged
+    assert run(base, (imu_t[:1], rx[:1], ry[:1], rz[:1])) > 0
+    # every point filtered out (range gate) -> empty cloud
+    assert run(dict(base, lidar_max_range=0.1), (imu_t, rx, ry, rz)) == 0
+    # ring bound: only rings < 4 survive; decimation by raw index
+    assert run(dict(base, n_scan=4, point_filter_num=7), (imu_t, rx, ry, rz)) > 0
+    # sweep starting after the last IMU sample / before the first one (findRotation's two clamps, IP:514)
+    assert run(base, (imu_t, rx, ry, rz), t_scan=t0 + 10.0) > 0
+    assert run(base, (imu_t, rx, ry, rz), t_scan=t0 - 10.0) > 0
+    # empty input
+    assert run(base, (imu_t, rx, ry, rz), sc=scan[:0]) == 0
+
+
+def test_context_reuse_and_errors(gpu, oracle, small_case):
+    from lio_slam_b200 import liogpu as L
+    # shrinking and growing inputs on one context (buffers are reused)
+    for n in (5000, 100, 20000, 31, 12000):
+        want, _ = oracle.voxel_grid(small_case["scan4"][:n], 0.4)
+        got, _ = gpu.voxel_downsample(small_case["scan4"][:n], 0.4)
+        assert biteq(got, want)
+    with pytest.raises(L.LioGpuError):          # leaf must be positive
+        gpu.voxel_downsample(small_case["scan4"], 0.0)
+    with pytest.raises(L.LioGpuError):          # max_iter out of range
+        gpu.set_local_map(small_case["map4"]); gpu.scan2map(small_case["scan4"], small_case["guess"], max_iter=31)
+    with pytest.raises(L.LioGpuError):          # no resident cloud yet on a fresh context
+        g2 = L.LioGpu()
+        try:
+            g2.set_local_map(small_case["map4"]); g2.scan2map(L.RESIDENT, small_case["guess"])
+        finally:
+            g2.close()
+    g3 = L.LioGpu()
+    try:
+        with pytest.raises(L.LioGpuError) as e:  # registration before any map
+            g3.scan2map(small_case["scan4"], small_case["guess"])
+        assert e.value.status == L.E_NO_MAP
+    finally:
+        g3.close()
+
+
+def test_sparse_map_single_phase_and_seeds(oracle, world):
+    # leaf-0.5 map (no phase-1 gate: every point goes through the warp-cooperative kernel on iteration 0, the
+    # seeded main kernel from iteration 1) with a large initial error so that several iterations run
+    from lio_slam_b200.liogpu import LioGpu
+    g = LioGpu(surrounding_keyframe_map_leaf_size=0.5)
+    try:
+        pose_gt = synth.path_pose(0.1)
+        scan4 = synth.to_packed(synth.make_scan(world, pose_gt, 16, seed=17, cols=900))
+        map4 = synth.make_local_map(world, 16, 20000, 0.5, seed=4, s0=-0.4, cols=900, max_poses=32)
+        ds, _ = oracle.voxel_grid(scan4, 0.4)
+        guess = synth.perturbed_guess(pose_gt, 3, rot_deg=(1.0, 1.0, 2.5), trans=(0.3, 0.3, 0.1))
+        ref_pose, ref_P, ref_info = oracle.scan2map(map4, ds, guess, threads=8)
+        g.set_local_map(map4)
+        pose, P, info = g.scan2map(ds, guess)
+        assert ref_info["iterations"] >= 4
+        assert info["iterations"] == ref_info["iterations"] and np.array_equal(info["nsel_hist"], ref_info["nsel_hist"])
+        assert np.abs(pose[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose[3:] - ref_pose[3:]).max() <= 1e-4
+        assert np.abs(info["pose_hist"] - ref_info["pose_hist"]).max() <= 1e-4
+        assert info["seeded"] > 0.5 * ds.shape[0]
+    finally:
+        g.close()
