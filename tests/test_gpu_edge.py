@@ -205,3 +205,39 @@ def test_sparse_map_single_phase_and_seeds(oracle, world):
         assert info["seeded"] > 0.5 * ds.shape[0]
     finally:
         g.close()
+
+
+def test_pinned_host_sweep_identical(oracle, world):
+    # a sweep in PINNED host memory (liogpu_host_alloc), as 32-byte records and as packed float4, must give
+    # the same bits as the pageable path
+    import ctypes as C
+    from lio_slam_b200.liogpu import LioGpu, load_library
+    lib = load_library()
+    g = LioGpu(surrounding_keyframe_map_leaf_size=0.2)
+    try:
+        pose_gt = synth.path_pose(0.1)
+        scan = synth.xyzirt_to_xyzi(synth.make_scan(world, pose_gt, 64, seed=41))          # 115,200 records of 32 B
+        n = scan.shape[0]
+        assert n >= 65536
+        map4 = synth.make_local_map(world, 64, 150000, 0.2, seed=2, s0=-0.4, max_poses=8)
+        guess = synth.perturbed_guess(pose_gt, 9)
+        g.set_local_map(map4)
+        pose_a, P_a, info_a = g.scan2map(scan, guess)                                        # pageable numpy buffer
+        ptr = lib.liogpu_host_alloc(C.c_ulonglong(n * 32))
+        assert ptr
+        try:
+            C.memmove(ptr, scan.ctypes.data, n * 32)
+            pose_b, P_b, info_b = g.scan2map((ptr, n, 32), guess)                             # pinned 32-byte records
+            packed = synth.to_packed(scan)
+            C.memmove(ptr, packed.ctypes.data, n * 16)
+            pose_c, P_c, info_c = g.scan2map((ptr, n, 16), guess)                             # pinned, packed float4
+        finally:
+            lib.liogpu_host_free(C.c_void_p(ptr))
+        for pose_x, info_x in ((pose_b, info_b), (pose_c, info_c)):
+            assert np.array_equal(pose_a, pose_x) and info_a["iterations"] == info_x["iterations"]
+            assert np.array_equal(info_a["JtJ"], info_x["JtJ"]) and np.array_equal(info_a["nsel_hist"], info_x["nsel_hist"])
+        ref_pose, _, ref_info = oracle.scan2map(map4, synth.to_packed(scan), guess, threads=8)
+        assert ref_info["iterations"] == info_a["iterations"]
+        assert np.abs(pose_a[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose_a[3:] - ref_pose[3:]).max() <= 1e-4
+    finally:
+        g.close()
