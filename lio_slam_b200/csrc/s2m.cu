@@ -1100,7 +1100,7 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
   // (a launch that finds `done` set exits at once), then the state block is read back — the same single
   // read-back a converged registration needs anyway.  Only scans that need more than S2M_CHUNK iterations
   // pay a second round trip.
-  const int S2M_CHUNK = 6;
+  const int S2M_CHUNK = 5;
   int launched = 0;
   float prof_main_ms = 0.f, prof_left_ms = 0.f;
   int prof_main_n = 0, prof_left_n = 0;
