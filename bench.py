@@ -168,7 +168,7 @@ def main():
     name = args.workload
     w = WORKLOADS[name]
     config = {"workload": f"{name}: {w['desc']}", "beams": w["beams"], "n_map": w["n_map"], "map_leaf": w["map_leaf"],
-              "max_iter": MAX_ITER, "sequences": "one independent sequence per GPU",
+              "max_iter": MAX_ITER, "sequences": "one independent sequence per GPU (every rank replays the same synthetic sequence)",
               "l2": "flushed (512 MiB write) between timed steps, outside the timed events"}
 
     if args.impl == "reference":
@@ -202,7 +202,9 @@ def main():
     import ctypes as C
 
     n_scans = 4
-    map4, scans, guesses = make_workload(name, rank, n_scans)
+    # every rank runs the SAME synthetic sequence (its own copy, its own GPU, no communication): N-GPU work is
+    # then exactly N x the 1-GPU work and the scaling number is not blurred by data-dependent iteration counts
+    map4, scans, guesses = make_workload(name, 0, n_scans)
     nq = int(scans[0].shape[0])
     config["n_query"] = nq
     if os.environ.get("LIOGPU_BENCH_PRESORT"):  # experiment: spatially coherent query order

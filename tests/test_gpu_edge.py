@@ -241,3 +241,52 @@ def test_pinned_host_sweep_identical(oracle, world):
         assert np.abs(pose_a[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose_a[3:] - ref_pose[3:]).max() <= 1e-4
     finally:
         g.close()
+
+
+def test_full_size_config3_parity(oracle):
+    # BASELINE configs[2] at full size: 128-beam sweep (230,400 points) vs a 500,000-point map, against the
+    # oracle with its exact KD-tree (brute force would take minutes).  Per-point results on one
+    # surfOptimization pass, then the whole loop.
+    import bench
+    from lio_slam_b200.liogpu import LioGpu
+    map4, scans, guesses = bench.make_workload("cfg3", 0, 1)
+    assert scans[0].shape[0] == 230400 and map4.shape[0] == 500000
+    g = LioGpu(n_scan=128, surrounding_keyframe_map_leaf_size=0.2)
+    try:
+        h = oracle.index_build(map4)
+        ref = oracle.surf_optimization(map4, scans[0], pose6=guesses[0], handle=h, threads=16)
+        g.set_local_map(map4)
+        got = g.surf_optimization(scans[0], pose6=guesses[0])
+        gate = ref["nn_d2"][:, 4] < 1.0
+        assert gate.mean() > 0.99
+        assert np.array_equal(got["nn_idx"][gate], ref["nn_idx"][gate])
+        assert biteq(got["nn_d2"][gate], ref["nn_d2"][gate])
+        assert np.array_equal(got["flag"], ref["flag"]) and biteq(got["coeff"], ref["coeff"])
+        assert np.array_equal(got["tie"][gate], ref["tie"][gate])
+        ref_pose, ref_P, ref_info = oracle.scan2map(map4, scans[0], guesses[0], threads=16, handle=h)
+        oracle.index_free(h)
+        pose, P, info = g.scan2map(scans[0], guesses[0])
+        assert info["iterations"] == ref_info["iterations"] and np.array_equal(info["nsel_hist"], ref_info["nsel_hist"])
+        assert np.abs(pose[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose[3:] - ref_pose[3:]).max() <= 1e-4
+        assert np.abs(info["JtJ"] - ref_info["JtJ"]).max() <= 1e-5 * np.abs(ref_info["JtJ"]).max()
+        assert info["tie_queries"] == ref_info["tie_queries"] and info["is_degenerate"] == ref_info["is_degenerate"]
+        print("cfg3 full size: iterations", info["iterations"], "n_sel", info["n_sel"], "pose bit-equal",
+              np.array_equal(pose, ref_pose), "JtJ max rel", float(np.abs(info["JtJ"] - ref_info["JtJ"]).max() / np.abs(ref_info["JtJ"]).max()))
+    finally:
+        g.close()
+
+
+def test_full_size_config4_voxel_5M(gpu, oracle):
+    # BASELINE configs[3] size: 5,000,000 points (walls + ground layout, heavy overlap), leaf 0.5 and 0.2
+    rng = np.random.default_rng(44)
+    n = 5_000_000
+    xy = rng.uniform(-60, 60, (n, 2))
+    z = np.where(rng.uniform(size=n) < 0.6, rng.normal(0, 0.02, n), rng.uniform(0, 12, n))
+    near = rng.uniform(size=n) < 0.3                       # a dense blob near the sensor: voxels with 1e4+ members
+    xy[near] = rng.normal(0, 3.0, (int(near.sum()), 2))
+    cloud = np.column_stack([xy, z, rng.uniform(0, 100, n)]).astype(np.float32)
+    for leaf in (0.5, 0.2):
+        want, ov = oracle.voxel_grid(cloud, leaf)
+        got, st = gpu.voxel_downsample(cloud, leaf)
+        assert not ov and biteq(got, want), leaf
+    print("5M voxel: device ms", gpu.last_gpu_ms(), "voxels", want.shape[0])
