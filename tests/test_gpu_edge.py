@@ -290,3 +290,43 @@ def test_full_size_config4_voxel_5M(gpu, oracle):
         got, st = gpu.voxel_downsample(cloud, leaf)
         assert not ov and biteq(got, want), leaf
     print("5M voxel: device ms", gpu.last_gpu_ms(), "voxels", want.shape[0])
+
+
+def test_large_scale_1p2M_queries_1p4M_map(oracle):
+    # beyond BASELINE sizes: 1.2 M sweep points (more than 4096 thread blocks: the leftover kernel's segment-offset
+    # table no longer fits its shared-memory fast path) against a 1.4 M-point map; spot-checked against the oracle
+    from lio_slam_b200.liogpu import LioGpu
+    rng = np.random.default_rng(77)
+
+    def surfaces(n, noise):
+        k = n // 3
+        g = np.column_stack([rng.uniform(-80, 80, k), rng.uniform(-80, 80, k), rng.normal(0, noise, k)])
+        w1 = np.column_stack([rng.uniform(-80, 80, k), np.full(k, 35.0) + rng.normal(0, noise, k), rng.uniform(0, 15, k)])
+        w2 = np.column_stack([np.full(n - 2 * k, -40.0) + rng.normal(0, noise, n - 2 * k), rng.uniform(-80, 80, n - 2 * k), rng.uniform(0, 15, n - 2 * k)])
+        return np.concatenate([g, w1, w2])
+    raw = np.column_stack([surfaces(12_000_000, 0.01), np.zeros(12_000_000)]).astype(np.float32)
+    g = LioGpu(surrounding_keyframe_map_leaf_size=0.2)
+    try:
+        map4, _ = g.voxel_downsample(raw, 0.2)
+        assert map4.shape[0] > 1_000_000
+        q = np.column_stack([surfaces(1_200_000, 0.02), np.ones(1_200_000)]).astype(np.float32)
+        q = q[rng.permutation(q.shape[0])]
+        pose = np.array([0.002, -0.003, 0.004, 0.05, -0.04, 0.02], np.float32)
+        g.set_local_map(map4)
+        got = g.surf_optimization(q, pose6=pose)
+        sub = rng.choice(q.shape[0], 20000, replace=False)
+        h = oracle.index_build(map4)
+        ref = oracle.surf_optimization(map4, q[sub], pose6=pose, handle=h, threads=16)
+        gate = ref["nn_d2"][:, 4] < 1.0
+        assert gate.mean() > 0.9
+        assert np.array_equal(got["nn_idx"][sub][gate], ref["nn_idx"][gate])
+        assert biteq(got["nn_d2"][sub][gate], ref["nn_d2"][gate])
+        assert np.array_equal(got["flag"][sub], ref["flag"]) and biteq(got["coeff"][sub], ref["coeff"])
+        ref_pose, _, ref_info = oracle.scan2map(map4, q, pose, threads=16, handle=h)
+        oracle.index_free(h)
+        pose_g, _, info = g.scan2map(q, pose)
+        assert info["iterations"] == ref_info["iterations"] and np.array_equal(info["nsel_hist"], ref_info["nsel_hist"])
+        assert np.abs(pose_g[:3] - ref_pose[:3]).max() <= 1e-5 and np.abs(pose_g[3:] - ref_pose[3:]).max() <= 1e-4
+        print("1.2M x", map4.shape[0], "iterations", info["iterations"], "gpu loop ms", info["gpu_ms"], "bit-equal pose", np.array_equal(pose_g, ref_pose))
+    finally:
+        g.close()
