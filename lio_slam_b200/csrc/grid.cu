@@ -114,7 +114,9 @@ int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
   float gate1_d2 = r1 * r1;
   if (c->prm.knn_phase1_radius < 0.f || gate1_d2 >= 0.64f * gate_d2) gate1_d2 = gate_d2;  // single phase
   float cell = c->prm.knn_cell_size;
-  if (!(cell > 0.f)) cell = fminf(fmaxf(r1, 0.25f), 0.5f);
+  // dense map: cell edge = phase-1 radius (its reach box is then at most 3 x 3 rows of cells);
+  // sparse map (single phase): 1 m cells so that the full 1 m gate also fits a 3 x 3 box
+  if (!(cell > 0.f)) cell = (gate1_d2 < gate_d2) ? fminf(fmaxf(r1, 0.25f), 0.5f) : 1.0f;
   grid_setup_kernel<<<1, 32, 0, c->stream>>>(mm, cell, gate_d2, gate1_d2, 1u << 25, d_gp);
   c->launches += 1;
   GridParams* h_gp = reinterpret_cast<GridParams*>((char*)c->h_pinned + 2048);

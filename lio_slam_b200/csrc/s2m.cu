@@ -142,6 +142,75 @@ __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, c
   }
 }
 
+// Fast path of the per-thread search when the reach box covers at most 3 x 3 rows of cells (always the case
+// for the phase-1 gate and for a seeded search on a grid whose cell edge is the phase-1 radius): the
+// cell_start look-ups of ALL rows are issued together — one memory round trip instead of one per visited row —
+// and the rows are then walked centre-out with the usual pruning against the running 5th-best distance.
+// The x range of a row is fixed from the initial bound (a superset of what the tightened bound would give);
+// the extra candidates cost one compare each.  Returns false when the box is larger (caller falls back).
+__device__ __forceinline__ bool grid_knn5_box9(const float4 q, const GridParams& g, const float gate_d2,
+                                               const float4* __restrict__ map_sorted,
+                                               const uint32_t* __restrict__ cell_start, Top5& t) {
+  t.init(gate_d2);
+  const float s2 = 2.0f * g.slack;
+  const float reach = sqrtf(gate_d2) * 1.000001f + s2;
+  int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
+  int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
+  zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
+  ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
+  if (zmin > zmax || ymin > ymax) return true;  // nothing in reach
+  if (zmax - zmin > 2 || ymax - ymin > 2) return false;
+  // centre row first; the box is [c-1, c+1] at most, clipped
+  const int cz = min(max((int)floorf((q.z - g.oz) * g.inv_h), zmin), zmax);
+  const int cy = min(max((int)floorf((q.y - g.oy) * g.inv_h), ymin), ymax);
+  if (cz - zmin > 1 || zmax - cz > 1 || cy - ymin > 1 || ymax - cy > 1) return false;
+  uint32_t rs[9], re[9];
+  float rm2[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int dz = (k / 3 == 0) ? 0 : ((k / 3 == 1) ? -1 : 1);
+    const int dy = (k % 3 == 0) ? 0 : ((k % 3 == 1) ? -1 : 1);
+    const int z = cz + dz, y = cy + dy;
+    rs[k] = 0; re[k] = 0; rm2[k] = FLT_MAX;
+    if (z >= zmin && z <= zmax && y >= ymin && y <= ymax) {
+      const float zlo = g.oz + (float)z * g.h, ylo = g.oy + (float)y * g.h;
+      const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
+      const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
+      const float m2 = (gz * gz + gy * gy) * 0.999999f;
+      if (m2 <= gate_d2) {
+        const float r = sqrtf(gate_d2 - m2) * 1.000001f + s2;
+        int xlo = (int)floorf((q.x - r - g.ox) * g.inv_h);
+        int xhi = (int)floorf((q.x + r - g.ox) * g.inv_h);
+        xlo = max(xlo, 0);
+        xhi = min(xhi, g.nx - 1);
+        if (xlo <= xhi) {
+          const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+          rs[k] = __ldg(cell_start + row + xlo);
+          re[k] = __ldg(cell_start + row + xhi + 1);
+          rm2[k] = m2;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (rm2[k] > t.d(t.k4)) continue;  // also skips the rows that were never loaded (rm2 = FLT_MAX)
+    const uint32_t s = rs[k], e = re[k];
+    for (uint32_t j = s; j < e; j += 4) {
+      const uint32_t last = e - 1;
+      const float4 p0 = __ldg(map_sorted + j);
+      const float4 p1 = __ldg(map_sorted + min(j + 1, last));
+      const float4 p2 = __ldg(map_sorted + min(j + 2, last));
+      const float4 p3 = __ldg(map_sorted + min(j + 3, last));
+      t.offer(l2_simple(q, p0), __float_as_int(p0.w));
+      if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
+      if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
+      if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
+    }
+  }
+  return true;
+}
+
 __device__ __forceinline__ u64 warp_min_u64(const u64 v) {
   const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
   const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
@@ -777,7 +846,8 @@ s2m_main_kernel(const S2mArgs A) {
     const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
     Top5 t;
-    bool searched = false;
+    float gate_use = A.g.gate1_d2;                      // phase-1 gate (dense map)
+    bool can_search = A.g.gate1_d2 < A.g.gate_d2, is_seeded = false;
     if (s_iter > 0) {
       // Seeded search: the five neighbours of the previous iteration are real map points, so their
       // largest distance to the moved query bounds the true 5th-neighbour distance.  Searching inside
@@ -793,19 +863,25 @@ s2m_main_kernel(const S2mArgs A) {
         D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p4)));
         const float bound = __uint_as_float(__float_as_uint(D) + 1u);  // next float above D: the seeds stay inside
         if (bound <= A.g.gate_d2) {
-          grid_knn5(sel, A.g, bound, A.map_sorted, A.cell_start, t);
-          searched = true;
+          gate_use = bound;
+          can_search = true;
+          is_seeded = true;
           ++seeded;
         }
       }
     }
-    if (!searched) {
-      if (A.g.gate1_d2 < A.g.gate_d2) {
-        grid_knn5(sel, A.g, A.g.gate1_d2, A.map_sorted, A.cell_start, t);
-        need2 = !(t.d(t.k4) < A.g.gate1_d2);
-      } else {
-        need2 = true;
-      }
+    if (can_search) {
+#ifndef S2M_NO_BOX9
+      // dense map: the row-by-row walk (x ranges tightened as the bound shrinks) executes fewer instructions
+      // and the kernel is issue bound; sparse map (1 m cells, few points per row): the search is latency
+      // bound and the all-rows-at-once variant wins
+      const bool sparse = !(A.g.gate1_d2 < A.g.gate_d2);
+      if (!sparse || !grid_knn5_box9(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
+#endif
+        grid_knn5(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+      need2 = !is_seeded && !(t.d(t.k4) < A.g.gate1_d2);
+    } else {
+      need2 = true;
     }
     if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
   }
