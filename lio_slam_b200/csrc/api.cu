@@ -155,7 +155,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.fail_buf, &c.prev_nn, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
+                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
   for (DevBuf* b : bufs) b->release();
   for (auto& kv : c.keyframes) kv.second.first.release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);

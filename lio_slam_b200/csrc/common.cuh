@@ -112,7 +112,7 @@ struct Ctx {
   // sort + scan scratch
   DevBuf keys0, keys1, vals0, vals1, counters, scan_tmp, seg_flag, seg_start;
   // small device structs
-  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf, prev_nn;
+  DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf, prev_nn, hopeless;
   // per-point debug outputs of surf_optimization
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
   // pinned host mirrors

@@ -224,18 +224,23 @@ __device__ __forceinline__ u64 warp_min_u64(const u64 v) {
 // prefix sum and handed out one per lane, so the candidate loads are in flight together too.  Each lane
 // keeps the best 5 of the candidates it saw; the lanes' lists are merged with five warp-wide minima.
 // The result is identical to the sequential search: a set selection under the total order (d2, index).
-__device__ __forceinline__ void warp_knn5(const float4 q, const GridParams& g, const float4* __restrict__ map_sorted,
-                                          const uint32_t* __restrict__ cell_start, const int lane, Top5& out) {
+// gate_ext_d2 >= gate_d2: every map point closer than sqrt(gate_ext_d2) is visited and COUNTED (return value,
+// warp-uniform), while only points inside gate_d2 compete for the five slots.  The count feeds the
+// "hopeless point" rule of the main kernel (see HOPELESS_* below).
+__device__ __forceinline__ int warp_knn5(const float4 q, const GridParams& g, const float gate_ext_d2,
+                                         const float4* __restrict__ map_sorted,
+                                         const uint32_t* __restrict__ cell_start, const int lane, Top5& out) {
   Top5 t;
   t.init(g.gate_d2);
   out.init(g.gate_d2);
+  int n_ext = 0;
   const float s2 = 2.0f * g.slack;
-  const float reach = sqrtf(g.gate_d2) * 1.000001f + s2;
+  const float reach = sqrtf(gate_ext_d2) * 1.000001f + s2;
   int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
   int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
   zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
   ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
-  if (zmin > zmax || ymin > ymax) return;
+  if (zmin > zmax || ymin > ymax) return 0;
   const int nys = ymax - ymin + 1;
   const int nrows = (zmax - zmin + 1) * nys;
   for (int base = 0; base < nrows; base += 32) {
@@ -247,8 +252,8 @@ __device__ __forceinline__ void warp_knn5(const float4 q, const GridParams& g, c
       const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
       const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
       const float m2 = (gz * gz + gy * gy) * 0.999999f;
-      if (m2 <= g.gate_d2) {
-        const float rr = sqrtf(g.gate_d2 - m2) * 1.000001f + s2;
+      if (m2 <= gate_ext_d2) {
+        const float rr = sqrtf(gate_ext_d2 - m2) * 1.000001f + s2;
         int xlo = (int)floorf((q.x - rr - g.ox) * g.inv_h);
         int xhi = (int)floorf((q.x + rr - g.ox) * g.inv_h);
         xlo = max(xlo, 0);
@@ -283,10 +288,14 @@ __device__ __forceinline__ void warp_knn5(const float4 q, const GridParams& g, c
       if (c < total) {
         const uint32_t j = row_s + (c - (row_incl - row_cnt));
         const float4 p = __ldg(map_sorted + j);
-        t.offer(l2_simple(q, p), __float_as_int(p.w));
+        const float d2 = l2_simple(q, p);
+        if (d2 < gate_ext_d2) ++n_ext;
+        t.offer(d2, __float_as_int(p.w));
       }
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_ext += __shfl_xor_sync(0xffffffffu, n_ext, o);
   // merge: five times take the smallest head over the lanes and pop it from its owner's list
   u64 res[5];
 #pragma unroll
@@ -306,7 +315,16 @@ __device__ __forceinline__ void warp_knn5(const float4 q, const GridParams& g, c
   for (int o = 16; o > 0; o >>= 1) rj = fminf(rj, __shfl_xor_sync(0xffffffffu, rj, o));
   out.k0 = res[0]; out.k1 = res[1]; out.k2 = res[2]; out.k3 = res[3]; out.k4 = res[4];
   out.rej = rj;
+  return n_ext;
 }
+
+// "Hopeless" points.  A sweep point with fewer than five map points within 1 m is dropped by surfOptimization
+// (:1641) — typically the far part of a sweep that lies outside the 50 m local map — but finding that out costs a
+// full-gate search in every iteration.  The leftover kernel therefore also counts the map points within
+// 1 m + HOPELESS_MARGIN of the point; if even that count is below five, then for as long as the point has moved
+// less than the margin (minus 1 mm for rounding) since then, fewer than five map points can lie within 1 m of
+// it (triangle inequality), and the main kernel skips it without searching.  Exact, not heuristic.
+constexpr float HOPELESS_MARGIN = 0.25f;
 
 // ---- the 6x6 tail of LMOptimization (mapOptmization.cpp:1721-1835), executed by ONE WARP ----
 // A single thread walking these 6x6 routines through local memory cost ~90 us per iteration (~170 us on
@@ -755,6 +773,7 @@ struct S2mArgs {
   int mode;
   int main_blocks;
   int* prev_nn;            // [5][nq] neighbours found by the previous iteration (-1: none), SoA
+  float4* hopeless;        // [nq] (x,y,z of the point when it was found hopeless, w = 1) or w = 0
 };
 
 struct RowAcc {  // which product of the staged row a reducing thread owns
@@ -847,12 +866,20 @@ s2m_main_kernel(const S2mArgs A) {
     const float4 sel = apply_T(sT, ori);
     Top5 t;
     float gate_use = A.g.gate1_d2;                      // phase-1 gate (dense map)
-    bool can_search = A.g.gate1_d2 < A.g.gate_d2, is_seeded = false;
+    bool can_search = A.g.gate1_d2 < A.g.gate_d2, is_seeded = false, skip = false;
     if (s_iter > 0) {
       // Seeded search: the five neighbours of the previous iteration are real map points, so their
       // largest distance to the moved query bounds the true 5th-neighbour distance.  Searching inside
       // that bound is exact, prunes almost every row, and needs no second phase.
       const int p0 = A.prev_nn[i];
+      if (p0 < 0) {
+        const float4 hr = A.hopeless[i];
+        if (hr.w > 0.f) {
+          const float dx = sel.x - hr.x, dy = sel.y - hr.y, dz = sel.z - hr.z;
+          const float lim = HOPELESS_MARGIN - 1e-3f;
+          skip = (dx * dx + dy * dy + dz * dz) < lim * lim;  // still cannot have 5 neighbours within the gate
+        }
+      }
       if (p0 >= 0) {
         const int p1 = A.prev_nn[(size_t)A.nq + i], p2 = A.prev_nn[2 * (size_t)A.nq + i];
         const int p3 = A.prev_nn[3 * (size_t)A.nq + i], p4 = A.prev_nn[4 * (size_t)A.nq + i];
@@ -870,7 +897,10 @@ s2m_main_kernel(const S2mArgs A) {
         }
       }
     }
-    if (can_search) {
+    if (skip) {
+      t.init(A.g.gate_d2);  // "not found": flag false, no seeds for the next iteration, marker kept
+      need2 = false;
+    } else if (can_search) {
 #ifndef S2M_NO_BOX9
       // dense map: the row-by-row walk (x ranges tightened as the bound shrinks) executes fewer instructions
       // and the kernel is issue bound; sparse map (1 m cells, few points per row): the search is latency
@@ -1038,15 +1068,21 @@ s2m_left_kernel(const S2mArgs A) {
       if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
       Top5 t;
       t.init(A.g.gate_d2);
+      int my_ext = 0;
       for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
         float4 q;
         q.x = __shfl_sync(0xffffffffu, sel.x, j); q.y = __shfl_sync(0xffffffffu, sel.y, j);
         q.z = __shfl_sync(0xffffffffu, sel.z, j); q.w = 0.f;
         Top5 tj;
-        warp_knn5(q, A.g, A.map_sorted, A.cell_start, lane, tj);
-        if (lane == j) t = tj;
+        const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;
+        const int n_ext = warp_knn5(q, A.g, ge * ge, A.map_sorted, A.cell_start, lane, tj);
+        if (lane == j) { t = tj; my_ext = n_ext; }
       }
-      if (mine >= 0) finish_point(A, mine, ori, sel, t, sTrig, row, rhs, flag, tie);
+      if (mine >= 0) {
+        finish_point(A, mine, ori, sel, t, sTrig, row, rhs, flag, tie);
+        const bool hopeless = !(t.d(t.k4) < A.g.gate_d2) && my_ext < 5;
+        A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, hopeless ? 1.f : 0.f);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
@@ -1145,6 +1181,8 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   A.ticket = c->block_counter.as<unsigned>();
   LIOGPU_CUDA_OK(c, c->prev_nn.reserve((size_t)5 * (size_t)(n > 0 ? n : 1) * sizeof(int)));
   A.prev_nn = c->prev_nn.as<int>();
+  LIOGPU_CUDA_OK(c, c->hopeless.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4)));
+  A.hopeless = c->hopeless.as<float4>();
   A.T_override = nullptr;
   A.dbg = SurfDebugOut{nullptr, nullptr, nullptr, nullptr, nullptr};
   A.mode = 0;
