@@ -50,7 +50,9 @@ typedef struct liogpu_ctx liogpu_ctx;
  * HBM as this context's resident cloud"; passed as an INPUT cloud pointer (n and stride are then ignored) to
  * liogpu_voxel_downsample, liogpu_scan2map, liogpu_downsample_scan2map, liogpu_surf_optimization or
  * liogpu_keyframe_put it means "use the resident cloud".  A co-located imageProjection + mapOptimization
- * thus moves a sweep over PCIe once (the raw XYZIRT records) and nothing else. */
+ * thus moves a sweep over PCIe once (the raw XYZIRT records) and nothing else.  The resident cloud lives in the
+ * context's scratch buffers: a later call that reuses its buffer for something else invalidates it (a subsequent
+ * LIOGPU_DEVICE_RESIDENT input then fails with LIOGPU_E_INVALID rather than reading other data). */
 #define LIOGPU_DEVICE_RESIDENT ((void*)(unsigned long long)1)
 
 /* Parameters the hot path reads from ParamServer (UT:199-331); defaults are UT's compiled-in ones.

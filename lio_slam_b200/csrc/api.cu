@@ -73,6 +73,12 @@ int store_cloud(Ctx* c, const float4* src, int n, void* dst, int stride) {
   return LIOGPU_OK;
 }
 
+// A call that is about to overwrite `buf` without declaring it the new resident cloud invalidates a resident
+// cloud that lives there: a later LIOGPU_DEVICE_RESIDENT use then fails loudly instead of reading other data.
+void clobber(Ctx* c, DevBuf* buf) {
+  if (c->resident == buf) { c->resident = nullptr; c->resident_n = 0; }
+}
+
 int enter(liogpu_ctx* ctx) {
   if (!ctx) return LIOGPU_E_INVALID;
   ctx->c.err.clear();
@@ -211,6 +217,7 @@ int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double
   }
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   int m = 0;
+  clobber(c, &c->dsk_scan);
   rc = deskew_dev(c, d_raw, n, stride, time_scan_cur, tab, n_imu, deskew_enabled, c->dsk_scan, &m);
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
@@ -237,6 +244,8 @@ int liogpu_transform_cloud(liogpu_ctx* ctx, const void* xyzi, int n, int stride,
   rc = load_cloud(c, xyzi, n, stride, c->scan4);
   if (rc) return rc;
   if (n == 0) return LIOGPU_OK;
+  clobber(c, &c->scan4);
+  clobber(c, &c->scan_ds4);
   LIOGPU_CUDA_OK(c, c->misc.reserve(256));
   LIOGPU_CUDA_OK(c, c->scan_ds4.reserve((size_t)n * sizeof(float4)));
   float* hp = reinterpret_cast<float*>((char*)c->h_pinned + 3200);
@@ -262,6 +271,8 @@ int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride
   rc = load_cloud(c, xyzi, n, stride, c->scan4);
   if (rc) return rc;
   if (n == 0) return LIOGPU_OK;
+  clobber(c, &c->scan4);
+  clobber(c, &c->scan_ds4);
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   int m = 0;
   bool overflow = false;
@@ -416,6 +427,7 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
   }
   rc = load_cloud(c, scan_ds, n, stride, c->scan_ds4);
   if (rc) return rc;
+  if (scan_ds != LIOGPU_DEVICE_RESIDENT) clobber(c, &c->scan_ds4);
   return scan2map_dev(c, c->scan_ds4.as<float4>(), n, pose_io, matP_io, degenerate_io, max_iter, info);
 }
 
@@ -429,6 +441,8 @@ int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int str
   *n_ds = 0;
   rc = load_cloud(c, scan, n, stride, c->scan4);
   if (rc) return rc;
+  clobber(c, &c->scan4);
+  clobber(c, &c->scan_ds4);
   int m = 0;
   bool overflow = false;
   rc = voxel_downsample_dev(c, c->scan4.as<float4>(), n, c->prm.mapping_surf_leaf_size, c->scan_ds4, &m, &overflow);
@@ -477,6 +491,7 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
   }
   rc = load_cloud(c, scan_ds, n, stride, c->scan_ds4);
   if (rc) return rc;
+  if (scan_ds != LIOGPU_DEVICE_RESIDENT) clobber(c, &c->scan_ds4);
   return surf_optimization_dev(c, c->scan_ds4.as<float4>(), n, pose6, T12, nn_idx, nn_d2, coeff, flag, tie);
 }
 

@@ -34,30 +34,42 @@ void mapOptimization::extractSurroundingKeyFrames() {
   extractNearby();
 }
 
-// Host logic, as in the reference: which keyframes form the local map.  The key-pose VoxelGrid (leaf
-// surroundingKeyframeDensity, :1535-1541) keeps one pose per occupied voxel; with a few hundred poses this
-// stays on the host.  (:1542 replaces each centroid by its nearest key pose, so the result is a subset of
-// the key poses: the first pose seen in each voxel is taken here.)
+// Host logic, as in the reference (mapOptmization.cpp:1519-1554): which keyframes form the local map.
+//   1. radiusSearch around the last key pose (PCL returns the hits sorted by distance);
+//   2. downSizeFilterSurroundingKeyPoses (VoxelGrid, leaf surroundingKeyframeDensity) on those poses — here through
+//      liogpu_voxel_downsample, the same routine the path uses everywhere;
+//   3. each centroid is snapped to its nearest key pose (nearestKSearch(pt, 1), :1538-1542);
+//   4. every keyframe younger than 10 s is appended WITHOUT de-duplication (:1545-1551) — a keyframe listed twice
+//      is concatenated twice by extractCloud, exactly as in the reference.
 void mapOptimization::extractNearby() {
   const PointType& last = cloudKeyPoses3D.back();
-  std::vector<int> near;
-  for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i)
-    if (pointDistance(cloudKeyPoses3D[i], last) <= surroundingKeyframeSearchRadius) near.push_back(i);
-  std::vector<int> ids;
-  const float inv = 1.0f / surroundingKeyframeDensity;
-  std::vector<long long> seen;
-  for (int i : near) {
+  std::vector<std::pair<float, int>> hits;
+  for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
     const PointType& p = cloudKeyPoses3D[i];
-    const long long key = ((long long)std::floor(p.x * inv) * 73856093LL) ^ ((long long)std::floor(p.y * inv) * 19349663LL) ^
-                          ((long long)std::floor(p.z * inv) * 83492791LL);
-    if (std::find(seen.begin(), seen.end(), key) == seen.end()) { seen.push_back(key); ids.push_back(i); }
+    const float d2 = (p.x - last.x) * (p.x - last.x) + (p.y - last.y) * (p.y - last.y) + (p.z - last.z) * (p.z - last.z);
+    if (d2 <= surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius) hits.emplace_back(d2, i);
   }
-  for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {  // :1545-1551 keyframes younger than 10 s
-    if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) {
-      if (std::find(ids.begin(), ids.end(), i) == ids.end()) ids.push_back(i);
-    } else {
-      break;
+  std::sort(hits.begin(), hits.end());
+  Cloud surroundingKeyPoses, ds(hits.size());
+  for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+  int n_ds = 0;
+  lastStatus = liogpu_voxel_downsample(ctx_, surroundingKeyPoses.data(), (int)surroundingKeyPoses.size(), sizeof(PointType),
+                                       surroundingKeyframeDensity, ds.data(), sizeof(PointType), (int)ds.size(), &n_ds);
+  if (lastStatus < 0) n_ds = 0;
+  std::vector<int> ids;
+  for (int k = 0; k < n_ds; ++k) {
+    int best = 0;
+    float bd = 3.4e38f;
+    for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
+      const PointType& p = cloudKeyPoses3D[i];
+      const float d2 = (p.x - ds[k].x) * (p.x - ds[k].x) + (p.y - ds[k].y) * (p.y - ds[k].y) + (p.z - ds[k].z) * (p.z - ds[k].z);
+      if (d2 < bd) { bd = d2; best = i; }
     }
+    ids.push_back((int)cloudKeyPoses3D[best].intensity);
+  }
+  for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {
+    if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) ids.push_back(i);
+    else break;
   }
   surroundingKeyPosesDS = ids;
   extractCloud(ids);

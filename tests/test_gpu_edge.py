@@ -330,3 +330,22 @@ def test_large_scale_1p2M_queries_1p4M_map(oracle):
         print("1.2M x", map4.shape[0], "iterations", info["iterations"], "gpu loop ms", info["gpu_ms"], "bit-equal pose", np.array_equal(pose_g, ref_pose))
     finally:
         g.close()
+
+
+def test_resident_cloud_is_invalidated_when_clobbered(oracle, small_case):
+    # a call that reuses the buffer holding the resident cloud must invalidate it (never serve stale data)
+    from lio_slam_b200 import liogpu as L
+    g = L.LioGpu(mapping_surf_leaf_size=0.4)
+    try:
+        g.set_local_map(small_case["map4"])
+        n_ds, _ = g.voxel_downsample(small_case["scan4"], 0.4, keep_on_device=True)
+        assert g.resident_size() == n_ds > 0
+        want, _ = oracle.voxel_grid(small_case["scan4"], 0.4)
+        got = g.surf_optimization(L.RESIDENT, pose6=small_case["guess"])            # consuming it keeps it
+        assert got["flag"].shape[0] == want.shape[0] and g.resident_size() == n_ds
+        g.voxel_downsample(small_case["scan4"][:1000], 0.4)                           # reuses the same scratch
+        assert g.resident_size() == 0
+        with pytest.raises(L.LioGpuError):
+            g.scan2map(L.RESIDENT, small_case["guess"])
+    finally:
+        g.close()
