@@ -1,23 +1,30 @@
 // s2m.cu — the scan-to-map hot loop: surfOptimization + combineOptimizationCoeffs + LMOptimization
-// (mapOptmization.cpp:1618-1687, 1689-1700, 1702-1837) as ONE kernel per Gauss-Newton iteration.
+// (mapOptmization.cpp:1618-1687, 1689-1700, 1702-1837), two kernels per Gauss-Newton iteration, the whole loop
+// on the device.
 //
-// s2m_iter_kernel, one thread per scan point:
-//   1. pointAssociateToMap (:841-847) with the 3x4 transform built from the device-resident pose
-//   2. exact 5-NN inside the 1 m gate on the sorted grid (grid.cu): rows of x-adjacent cells are
-//      contiguous ranges of map_sorted; rows are visited centre-out and pruned against the current
-//      5th-best distance; distances are FLANN L2_Simple in f32 without FMA; ties -> lower map index
-//   3. 5x3 column-pivoted Householder plane fit, validity, weight s, coefficient (:1633-1684)
-//   4. Jacobian row (:1760-1778) staged in shared memory; the block reduces the 27 sums of
-//      A^T A (upper triangle) and A^T b in FP64 (cv::gemm accumulates f32 products in double)
-//   5. the last block to finish (threadfence + atomic ticket) adds the per-block partials in a fixed
-//      order and runs the 6x6 tail of LMOptimization on device: QR solve, Jacobi eigen + matP on
-//      iteration 0, degeneracy projection, pose update, convergence test (:1784-1835).
-// The pose, matP, isDegenerate and the iteration counter stay in HBM (LmDevState); the host enqueues
-// max_iter launches back to back and never reads anything until the loop is over — a launch that
-// finds `done` set returns immediately.  Compaction (:1689-1700) is unnecessary: rejected points
-// contribute exact zeros and the FP64 sums do not depend on the order.
+//   s2m_main_kernel   one thread per sweep point
+//     1. pointAssociateToMap (:841-847) with the device-resident 3x4 transform
+//     2. exact 5-NN on the sorted grid (grid.cu): rows of x-adjacent cells are contiguous ranges of map_sorted;
+//        rows are visited centre-out and pruned against the running 5th-best distance; distances are FLANN
+//        L2_Simple in f32 without FMA; ties -> lower map index.  Iteration 0 searches inside a small phase-1
+//        gate; iterations >= 1 inside the bound given by the previous iteration's neighbours (seeded search);
+//        points with too few map points around are skipped by the exact "hopeless" rule
+//     3. 5x3 column-pivoted Householder plane fit, validity, weight s, coefficient (:1633-1684)
+//     4. Jacobian row (:1760-1778) staged in shared memory; the block reduces the 27 sums of A^T A (upper
+//        triangle) and A^T b in FP64 (cv::gemm accumulates f32 products in double)
+//     5. points phase 1 could not settle go to a per-block segment of the leftover list
+//   s2m_left_kernel   warp-cooperative full-gate search of the leftovers (one per warp), fold of all partial
+//     sums in a fixed order, and — in the last block to finish — the 6x6 tail of LMOptimization
+//     (lm_finalize_warp): QR solve, degeneracy decision / matP on iteration 0, projection, pose update,
+//     convergence test (:1784-1835), next iteration's transform
+//   lm_matp_kernel    iteration 0's Jacobi eigen-decomposition + matP on a second stream when a rigorous
+//     certificate has already decided isDegenerate = false
 //
-// Algorithmic HBM bytes per launch: 16 B query + 5 x 16 B neighbours = 96 B per scan point.
+// The pose, matP, isDegenerate and the iteration counter stay in HBM (LmDevState); the host enqueues a chunk of
+// iterations back to back and reads the 1.8 KB state once — a launch that finds `done` set returns immediately.
+// Compaction (:1689-1700) is unnecessary: rejected points contribute exact zeros to the FP64 sums.
+//
+// Algorithmic HBM bytes per launch: 16 B query + 5 x 16 B neighbours = 96 B per sweep point.
 #include "common.cuh"
 #include "pose_math.cuh"
 

@@ -2,7 +2,8 @@
 //
 // Used by the VoxelGrid replacement (pcl::VoxelGrid sorts (voxel idx, point idx) pairs; SURVEY A.1
 // step 6 — the canonical order is the STABLE one, which is what an LSD radix sort delivers) and by
-// order-preserving compaction.  8 bits per pass; only ceil(key_bits/8) passes are run.
+// order-preserving compaction.  8 bits per pass; ceil(key_bits/8) passes when the host knows the key width,
+// otherwise four passes of which the ones beyond the device-side width degrade to a copy (no host round trip).
 //
 // Per pass, three launches:
 //   rs_hist_kernel    per-block digit histogram                     -> counters[digit][block]
