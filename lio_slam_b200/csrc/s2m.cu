@@ -852,6 +852,9 @@ s2m_main_kernel(const S2mArgs A) {
 
   __shared__ int s_done0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream
+  // was still in its single-block tail; nothing it wrote may be read before this returns.
+  cudaGridDependencySynchronize();
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
   if (tid == 32) {
     sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
@@ -1018,6 +1021,7 @@ s2m_left_kernel(const S2mArgs A) {
 
   __shared__ int s_done0, s_iter0, s_total0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cudaGridDependencySynchronize();  // see s2m_main_kernel
   // every global value the block needs is requested in one go (one L2 round trip instead of four)
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];
   if (tid == 32) {
@@ -1156,6 +1160,24 @@ s2m_left_kernel(const S2mArgs A) {
   }
 }
 
+// Both kernels of an iteration are launched with programmatic stream serialization: the next grid is scheduled
+// as the previous one drains (its last block is still reducing / solving the 6x6 system) and waits in
+// cudaGridDependencySynchronize(), which hides the launch latency between dependent kernels.
+template <class K>
+static cudaError_t launch_pdl(K kernel, int blocks, int threads, cudaStream_t stream, const S2mArgs& A) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, A);
+}
+
 static int check_grid(Ctx* c) {
   if (!c->grid_valid) { c->err = "no local map installed (call liogpu_set_local_map / liogpu_build_local_map)"; return LIOGPU_E_NO_MAP; }
   return LIOGPU_OK;
@@ -1238,9 +1260,9 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
     for (int it = 0; it < todo; ++it) {
       const bool first = launched + it == 0;
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
-      if (two_phase || !first) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+      if (two_phase || !first) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
-      s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
+      LIOGPU_CUDA_OK(c, launch_pdl(s2m_left_kernel, left_blocks, LEFT_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 2], c->stream));
       c->launches += (two_phase || !first) ? 2 : 1;
       if (first) {  // iteration 0's eigen analysis / matP off the critical path
