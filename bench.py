@@ -352,7 +352,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "e2e": {"value": e2e_value, "unit": "registrations/s", "ms_per_step": tot_e2e / args.steps,
-                    "h2d_bytes_per_step": nq * 32 + 1536, "d2h_bytes_per_step": 1536},
+                    "h2d_bytes_per_step": nq * 32 + 1616, "d2h_bytes_per_step": 1616},
             "gpu_launches": launches, "mean_lm_iterations": float(np.mean(iters)),
             "loop_ms_per_step": float(np.mean(loop_ms)), "wall_s_region1": wall_s,
             "roofline": roofline, "cpu_baseline": cb, "clocks": clocks}

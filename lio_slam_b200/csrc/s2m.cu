@@ -1367,3 +1367,4 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
 }
 
 }  // namespace liogpu
+static_assert(sizeof(liogpu::LmDevState) == 1616, "bench.py counts sizeof(LmDevState) bytes of H2D/D2H per registration");
