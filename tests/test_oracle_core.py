@@ -146,3 +146,22 @@ def test_deskew_invariants(oracle, world):
     idx = np.arange(raw.shape[0])
     keep2 = keep & (scan["ring"] % 2 == 0) & (idx % 3 == 0)
     assert biteq(out2, raw[keep2])
+
+
+def test_knn_against_scipy_ckdtree(oracle):
+    # an independent exact k-NN (scipy cKDTree, f64): same neighbour sets wherever the 5th/6th distances are
+    # not within f32 rounding of each other, same order, f32 distances equal to the f64 ones within 1 ulp-ish
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(21)
+    map4 = rng.uniform(-15, 15, (40000, 4)).astype(np.float32)
+    map4[:, 2] *= 0.05
+    q = rng.uniform(-15, 15, (5000, 4)).astype(np.float32)
+    q[:, 2] *= 0.05
+    idx, d2, tie = oracle.knn5(map4, q, threads=8)
+    dd, ii = cKDTree(map4[:, :3].astype(np.float64)).query(q[:, :3].astype(np.float64), k=6)
+    clear = (dd[:, 5] - dd[:, 4]) > 1e-5 * np.maximum(dd[:, 5], 1e-3)
+    inner = np.all(np.diff(dd[:, :5], axis=1) > 1e-5 * np.maximum(dd[:, 1:5], 1e-3), axis=1)
+    ok = clear & inner
+    assert ok.mean() > 0.95
+    assert np.array_equal(idx[ok], ii[ok, :5])
+    assert np.abs(np.sqrt(d2[ok].astype(np.float64)) - dd[ok, :5]).max() < 1e-5
