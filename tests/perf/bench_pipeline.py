@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lio_slam_b200 import synth  # noqa: E402
 from lio_slam_b200.liogpu import LioGpu, RESIDENT  # noqa: E402
