@@ -144,6 +144,51 @@ int liogpu_keyframe_count(const liogpu_ctx* ctx);
 int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k,
                            float leaf, int* n_map, void* xyzi_out, int out_stride, int cap_out);
 
+/* ---- publishLocalMap (MO:2442-2541), called after every registration (MO:504) ----
+ * Filter settings of the node (utility.h:219-229, set up at MO:293-304). */
+typedef struct liogpu_local_map_params {
+  float local_map_left;          /* localMapLeft   UT:221: PassThrough x in [-left, right]  (MO:296-297) */
+  float local_map_right;         /* localMapRight  UT:223 */
+  float local_map_front;         /* localMapFront  UT:220: PassThrough y in [-back, front]  (MO:300-301) */
+  float local_map_back;          /* localMapBack   UT:222 */
+  int   use_removing_outliers;   /* useRemovingOutliers UT:227 -> pcl::StatisticalOutlierRemoval (MO:2510-2516) */
+  int   mean_k;                  /* meanK UT:228 (1..31) */
+  float stddev_threshold;        /* stddevThreshold UT:229 */
+  int   use_down_sampling;       /* useDownSamplingLocalMap UT:224 -> VoxelGrid (MO:2517-2540) */
+  float local_mapping_surf_leaf_size; /* localMappingSurfLeafSize UT:226 */
+  float sor_cell_size;           /* tuning only (never changes results): cell edge of the outlier filter's
+                                    neighbour grid, <= 0 = automatic */
+  int   reserved[6];
+} liogpu_local_map_params;
+
+typedef struct liogpu_local_map_info {
+  int    n_concat;        /* points of the concatenated keyframes (globalMapCloud, MO:2463-2466) */
+  int    n_cropped;       /* after the two PassThrough filters (localMapCloud, MO:2502-2507) */
+  int    n_after_sor;     /* after the outlier filter (= n_cropped when it is off) */
+  int    n_out;           /* published points */
+  int    leaf_overflow;   /* 1: the VoxelGrid overflow guard fired, cloud published un-downsampled (q4) */
+  int    sor_borderline;  /* points whose mean distance is within 1e-9 (relative) of the threshold: the only
+                             ones a different summation order of the statistics could flip */
+  double sor_mean, sor_stddev, sor_threshold; /* statistics of the mean k-NN distances */
+  float  gpu_ms;
+  int    sor_leftover;    /* points finished by the wide (warp-cooperative) neighbour search */
+  int    sor_exhaustive;  /* of those, isolated points that needed the exhaustive search */
+  int    reserved[4];
+} liogpu_local_map_info;
+
+/* UT:219-229 defaults. */
+void liogpu_default_local_map_params(liogpu_local_map_params* p);
+
+/* publishLocalMap (MO:2442-2541): transform the k named keyframes (the host passes the last
+ * localMapKeyFramesNumber ids, MO:2462) by their poses and concatenate them, move the cloud into the vehicle's
+ * yaw-aligned frame of pose_now = transformTobeMapped (thisPoseX/Y/Z/Yaw, MO:2249-2254, 2474-2489), crop it with
+ * PassThrough x then y, optionally remove statistical outliers and VoxelGrid it.  The result (tempCloud,
+ * MO:2541) is written to xyzi_out in the reference's order.  info may be NULL. */
+int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k,
+                             const float pose_now[6], const liogpu_local_map_params* params,
+                             void* xyzi_out, int out_stride, int cap_out, int* n_out,
+                             liogpu_local_map_info* info);
+
 /* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);

@@ -3,6 +3,7 @@
 // without a usable CUDA device every entry point fails with LIOGPU_E_CUDA.
 #include "common.cuh"
 
+#include <cmath>
 #include <cstring>
 #include <new>
 
@@ -161,7 +162,9 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan};
+                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan,
+                    &c.lm_flag, &c.lm_pos, &c.lm_a, &c.lm_b, &c.lm_md, &c.lm_left, &c.lm_out, &c.lm_stats, &c.sor_setup,
+                    &c.sor_sorted, &c.sor_cell_start};
   for (DevBuf* b : bufs) b->release();
   for (auto& kv : c.keyframes) kv.second.first.release();
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
@@ -377,6 +380,112 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+void liogpu_default_local_map_params(liogpu_local_map_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->local_map_front = 70.0f;             // utility.h:220
+  p->local_map_left = 40.0f;              // :221
+  p->local_map_back = 20.0f;              // :222
+  p->local_map_right = 40.0f;             // :223
+  p->use_down_sampling = 1;               // :224
+  p->local_mapping_surf_leaf_size = 0.01f; // :226
+  p->use_removing_outliers = 1;           // :227
+  p->mean_k = 10;                         // :228
+  p->stddev_threshold = 1.0f;             // :229
+}
+
+int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, const float pose_now[6],
+                             const liogpu_local_map_params* params, void* xyzi_out, int out_stride, int cap_out,
+                             int* n_out, liogpu_local_map_info* info) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  liogpu_local_map_info local_info;
+  if (!info) info = &local_info;
+  std::memset(info, 0, sizeof(*info));
+  if (k < 0 || (k > 0 && (!ids || !pose6s)) || !pose_now || !params || !n_out) {
+    c->err = "liogpu_publish_local_map: bad arguments";
+    return LIOGPU_E_INVALID;
+  }
+  *n_out = 0;
+  if (params->use_removing_outliers && (params->mean_k < 1 || params->mean_k > 31)) {
+    c->err = "liogpu_publish_local_map: mean_k must be in 1..31";
+    return LIOGPU_E_INVALID;
+  }
+  if (params->use_down_sampling && !(params->local_mapping_surf_leaf_size > 0.f)) {
+    c->err = "liogpu_publish_local_map: leaf must be > 0";
+    return LIOGPU_E_INVALID;
+  }
+  if (k == 0) return LIOGPU_W_NO_KEYFRAMES;  // cloudKeyPoses3D->points.empty(), mapOptmization.cpp:2444
+  size_t total = 0;
+  for (int f = 0; f < k; ++f) {
+    auto it = c->keyframes.find(ids[f]);
+    if (it == c->keyframes.end()) { c->err = "liogpu_publish_local_map: unknown keyframe id"; return LIOGPU_E_NO_KEYFRAME; }
+    total += (size_t)it->second.second;
+  }
+  if (total > 0x7fffffffULL) { c->err = "local map too large"; return LIOGPU_E_INVALID; }
+  if ((size_t)k * 6 * sizeof(float) > 32768) {
+    c->err = "too many keyframes in one local map (max 1365)";
+    return LIOGPU_E_INVALID;
+  }
+  if (total == 0) return LIOGPU_OK;
+  // staging, same layout as liogpu_build_local_map
+  char* hp = (char*)c->h_pinned + 131072;
+  float* hposes = reinterpret_cast<float*>(hp);
+  int* hoffs = reinterpret_cast<int*>(hp + 32768);
+  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
+  std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
+  size_t off = 0;
+  for (int f = 0; f < k; ++f) {  // "+=" concatenation order (mapOptmization.cpp:2463-2466)
+    auto& kf = c->keyframes[ids[f]];
+    hoffs[f] = (int)off;
+    hsrcs[f] = kf.first.as<float4>();
+    off += (size_t)kf.second;
+  }
+  hoffs[k] = (int)off;
+  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));
+  char* dp = (char*)c->dbg_d2.p;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
+  // The yaw-aligned vehicle frame (mapOptmization.cpp:2474-2488), f32 like the reference; canonical trig = f64
+  // sin/cos rounded to f32 as everywhere in this library.  Rotation = Eigen::AngleAxisf(-yaw, UnitZ)
+  // .toRotationMatrix(): its zz entry is (1 - c) + c, which is not always exactly 1.
+  float yw[16];
+  {
+    const float yaw = pose_now[2], X = pose_now[3], Y = pose_now[4], Z = pose_now[5];
+    const float nyaw = -yaw;
+    const float cs = (float)cos((double)nyaw), sn = (float)sin((double)nyaw);
+    const float px = X * cs, py = Y * sn, qx = Y * cs, qy = X * sn;
+    const float tX = px - py;  // :2474
+    const float tY = qx + qy;  // :2475
+    const float tZ = Z;        // :2476
+    const float zz = (1.0f - cs) + cs;
+    const float m[12] = {cs, -sn, 0.f, -tX, sn, cs, 0.f, -tY, 0.f, 0.f, zz, -tZ};
+    for (int q = 0; q < 12; ++q) yw[q] = m[q];
+    yw[12] = -params->local_map_left;   // :297
+    yw[13] = params->local_map_right;
+    yw[14] = -params->local_map_back;   // :301
+    yw[15] = params->local_map_front;
+  }
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  const float4* result = nullptr;
+  int m = 0;
+  rc = publish_local_map_dev(c, reinterpret_cast<const float4* const*>(dp + 49152), reinterpret_cast<const int*>(dp + 32768),
+                             k, reinterpret_cast<const float*>(dp), reinterpret_cast<float*>(dp + 65536), (long long)total,
+                             yw, params, &result, &m, info);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_out = m;
+  if (xyzi_out && m > 0) {
+    if (m > cap_out) { c->err = "liogpu_publish_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, result, m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  info->gpu_ms = c->last_ms;
+  return info->leaf_overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
 }
 
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {

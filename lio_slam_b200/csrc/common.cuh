@@ -121,6 +121,8 @@ struct Ctx {
   std::map<int, std::pair<DevBuf, int>> keyframes;
   // deskew
   DevBuf imu_tab, dsk_flags, dsk_scan;
+  // publishLocalMap (localmap.cu): crop / outlier-filter scratch and the filter's own neighbour grid
+  DevBuf lm_flag, lm_pos, lm_a, lm_b, lm_md, lm_left, lm_out, lm_stats, sor_setup, sor_sorted, sor_cell_start;
   // device-resident hand-off (LIOGPU_DEVICE_RESIDENT)
   DevBuf* resident = nullptr;
   int resident_n = 0;
@@ -140,6 +142,7 @@ struct Ctx {
 cudaError_t launch_unpack(Ctx* c, const void* d_raw, int n, int stride, float4* out);
 cudaError_t launch_pack(Ctx* c, const float4* in, int n, void* d_raw, int stride);
 cudaError_t launch_transform(Ctx* c, const float4* in, int n, const float* d_pose6, float4* out);
+cudaError_t launch_pose_table(Ctx* c, const float* d_poses6, int k, float* d_T12);
 cudaError_t launch_transform_multi(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
                                    float* d_T12, long long total, float4* out);
 // --- sort.cu
@@ -151,6 +154,12 @@ cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm);
 int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& out, int* n_out, bool* overflow);
 // --- grid.cu
 int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint);
+int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2, float gate1_d2, DevBuf& setup,
+                    DevBuf& sorted, DevBuf& cell_start_buf, GridParams& host_gp);
+// --- localmap.cu
+int publish_local_map_dev(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
+                          float* d_T12, long long total, const float* h_yaw16, const liogpu_local_map_params* prm,
+                          const float4** result, int* n_result, liogpu_local_map_info* info);
 // --- s2m.cu
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info);

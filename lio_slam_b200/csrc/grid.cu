@@ -91,20 +91,49 @@ grid_gather_kernel(const float4* __restrict__ map4, const uint32_t* __restrict__
   map_sorted[j] = make_float4(p.x, p.y, p.z, __int_as_float((int)src));
 }
 
-int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
-  c->grid_valid = false;
-  c->n_map = n;
-  if (n <= 0) return LIOGPU_OK;
+// Builds the sorted-grid index of `pts` into the given buffers (the local-map index of the registration and the
+// self-index of publishLocalMap's outlier filter are two instances).  Synchronises the stream once to learn
+// the grid dimensions.
+int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2, float gate1_d2, DevBuf& setup,
+                    DevBuf& sorted, DevBuf& cell_start_buf, GridParams& host_gp) {
   LIOGPU_CUDA_OK(c, c->minmax.reserve(64));
-  LIOGPU_CUDA_OK(c, c->grid_setup.reserve(sizeof(GridParams)));
+  LIOGPU_CUDA_OK(c, setup.reserve(sizeof(GridParams)));
   LIOGPU_CUDA_OK(c, c->keys0.reserve((size_t)n * 4));
   LIOGPU_CUDA_OK(c, c->keys1.reserve((size_t)n * 4));
   LIOGPU_CUDA_OK(c, c->vals0.reserve((size_t)n * 4));
   LIOGPU_CUDA_OK(c, c->vals1.reserve((size_t)n * 4));
-  LIOGPU_CUDA_OK(c, c->map_sorted.reserve((size_t)n * sizeof(float4)));
+  LIOGPU_CUDA_OK(c, sorted.reserve((size_t)n * sizeof(float4)));
   unsigned* mm = c->minmax.as<unsigned>();
-  GridParams* d_gp = c->grid_setup.as<GridParams>();
-  LIOGPU_CUDA_OK(c, launch_minmax(c, map4, n, mm));
+  GridParams* d_gp = setup.as<GridParams>();
+  LIOGPU_CUDA_OK(c, launch_minmax(c, pts, n, mm));
+  grid_setup_kernel<<<1, 32, 0, c->stream>>>(mm, cell, gate_d2, gate1_d2, 1u << 25, d_gp);
+  c->launches += 1;
+  GridParams* h_gp = reinterpret_cast<GridParams*>((char*)c->h_pinned + 2048);
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, c->stream));
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  host_gp = *h_gp;
+  const GridParams& g = host_gp;
+  if (g.n_points <= 0) return LIOGPU_OK;
+  LIOGPU_CUDA_OK(c, cell_start_buf.reserve(((size_t)g.n_cells + 2) * sizeof(uint32_t)));
+  uint32_t* cell_start = cell_start_buf.as<uint32_t>();
+  LIOGPU_CUDA_OK(c, cudaMemsetAsync(cell_start, 0, ((size_t)g.n_cells + 2) * sizeof(uint32_t), c->stream));
+  grid_key_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, d_gp, c->keys0.as<uint32_t>(), cell_start);
+  c->launches++;
+  LIOGPU_CUDA_OK(c, exclusive_scan_u32(c, cell_start, cell_start, (int)g.n_cells + 1, nullptr));
+  int bits = 0;
+  while (bits < 32 && (g.n_cells >> bits) != 0u) ++bits;
+  uint32_t *skeys = nullptr, *sperm = nullptr;
+  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, bits, nullptr, &skeys, &sperm));
+  grid_gather_kernel<<<div_up(g.n_points, 256), 256, 0, c->stream>>>(pts, sperm, g.n_points, sorted.as<float4>());
+  c->launches++;
+  LIOGPU_CUDA_OK(c, cudaGetLastError());
+  return LIOGPU_OK;
+}
+
+int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
+  c->grid_valid = false;
+  c->n_map = n;
+  if (n <= 0) return LIOGPU_OK;
   // Tuning (results never depend on it): the first search phase looks inside r1 ~ twice the map's point
   // spacing (the VoxelGrid leaf), where a query on a mapped surface already finds its 5 neighbours; the
   // cell edge follows r1 so that phase 1 touches a 3x3x3 block of cells.
@@ -117,28 +146,8 @@ int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint) {
   // dense map: cell edge = phase-1 radius (its reach box is then at most 3 x 3 rows of cells);
   // sparse map (single phase): 1 m cells so that the full 1 m gate also fits a 3 x 3 box
   if (!(cell > 0.f)) cell = (gate1_d2 < gate_d2) ? fminf(fmaxf(r1, 0.25f), 0.5f) : 1.0f;
-  grid_setup_kernel<<<1, 32, 0, c->stream>>>(mm, cell, gate_d2, gate1_d2, 1u << 25, d_gp);
-  c->launches += 1;
-  GridParams* h_gp = reinterpret_cast<GridParams*>((char*)c->h_pinned + 2048);
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_gp, d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, c->stream));
-  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-  c->grid = *h_gp;
-  const GridParams& g = c->grid;
-  if (g.n_points <= 0) { c->grid_valid = true; return LIOGPU_OK; }
-  LIOGPU_CUDA_OK(c, c->cell_start.reserve(((size_t)g.n_cells + 2) * sizeof(uint32_t)));
-  uint32_t* cell_start = c->cell_start.as<uint32_t>();
-  LIOGPU_CUDA_OK(c, cudaMemsetAsync(cell_start, 0, ((size_t)g.n_cells + 2) * sizeof(uint32_t), c->stream));
-  grid_key_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(map4, n, d_gp, c->keys0.as<uint32_t>(), cell_start);
-  c->launches++;
-  LIOGPU_CUDA_OK(c, exclusive_scan_u32(c, cell_start, cell_start, (int)g.n_cells + 1, nullptr));
-  int bits = 0;
-  while (bits < 32 && (g.n_cells >> bits) != 0u) ++bits;
-  uint32_t *skeys = nullptr, *sperm = nullptr;
-  LIOGPU_CUDA_OK(c, radix_sort_pairs(c, n, bits, nullptr, &skeys, &sperm));
-  grid_gather_kernel<<<div_up(g.n_points, 256), 256, 0, c->stream>>>(map4, sperm, g.n_points,
-                                                                      c->map_sorted.as<float4>());
-  c->launches++;
-  LIOGPU_CUDA_OK(c, cudaGetLastError());
+  const int rc = grid_build_core(c, map4, n, cell, gate_d2, gate1_d2, c->grid_setup, c->map_sorted, c->cell_start, c->grid);
+  if (rc) return rc;
   c->grid_valid = true;
   return LIOGPU_OK;
 }

@@ -82,12 +82,19 @@ transform_multi_kernel(const float4* const* __restrict__ srcs, const int* __rest
   for (int q = 0; q < 12; ++q) T[q] = __ldg(T12 + 12 * lo + q);
   out[i] = apply_T(T, p);
 }
+cudaError_t launch_pose_table(Ctx* c, const float* d_poses6, int k, float* d_T12) {
+  if (k <= 0) return cudaSuccess;
+  pose_table_kernel<<<div_up(k, 128), 128, 0, c->stream>>>(d_poses6, k, d_T12);
+  c->launches++;
+  return cudaGetLastError();
+}
 cudaError_t launch_transform_multi(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
                                    float* d_T12, long long total, float4* out) {
   if (k <= 0 || total <= 0) return cudaSuccess;
-  pose_table_kernel<<<div_up(k, 128), 128, 0, c->stream>>>(d_poses6, k, d_T12);
+  cudaError_t e = launch_pose_table(c, d_poses6, k, d_T12);
+  if (e != cudaSuccess) return e;
   transform_multi_kernel<<<div_up(total, 256), 256, 0, c->stream>>>(d_srcs, d_offs, k, d_T12, total, out);
-  c->launches += 2;
+  c->launches++;
   return cudaGetLastError();
 }
 

@@ -41,12 +41,26 @@ class S2MInfo(C.Structure):
                 ("left_kernel_ms", C.c_float), ("main_kernel_launches", C.c_int), ("left_kernel_launches", C.c_int)]
 
 
+class LocalMapParams(C.Structure):
+    _fields_ = [("local_map_left", C.c_float), ("local_map_right", C.c_float), ("local_map_front", C.c_float),
+                ("local_map_back", C.c_float), ("use_removing_outliers", C.c_int), ("mean_k", C.c_int),
+                ("stddev_threshold", C.c_float), ("use_down_sampling", C.c_int),
+                ("local_mapping_surf_leaf_size", C.c_float), ("sor_cell_size", C.c_float), ("reserved", C.c_int * 6)]
+
+
+class LocalMapInfo(C.Structure):
+    _fields_ = [("n_concat", C.c_int), ("n_cropped", C.c_int), ("n_after_sor", C.c_int), ("n_out", C.c_int),
+                ("leaf_overflow", C.c_int), ("sor_borderline", C.c_int), ("sor_mean", C.c_double),
+                ("sor_stddev", C.c_double), ("sor_threshold", C.c_double), ("gpu_ms", C.c_float),
+                ("sor_leftover", C.c_int), ("sor_exhaustive", C.c_int), ("reserved", C.c_int * 4)]
+
+
 EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liogpu_destroy", "liogpu_last_error",
            "liogpu_host_alloc", "liogpu_host_free", "liogpu_deskew", "liogpu_transform_cloud",
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -89,6 +103,11 @@ def load_library() -> C.CDLL:
     lib.liogpu_build_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                                            C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_default_local_map_params.argtypes = [C.POINTER(LocalMapParams)]
+    lib.liogpu_default_local_map_params.restype = None
+    lib.liogpu_publish_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                             C.POINTER(LocalMapParams), C.c_void_p, C.c_int, C.c_int,
+                                             C.POINTER(C.c_int), C.POINTER(LocalMapInfo)]
     lib.liogpu_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo)]
     lib.liogpu_downsample_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -103,6 +122,15 @@ def load_library() -> C.CDLL:
 def default_params(**over) -> Params:
     p = Params()
     load_library().liogpu_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def local_map_params(**over) -> LocalMapParams:
+    """utility.h:219-229 defaults, with keyword overrides."""
+    p = LocalMapParams()
+    load_library().liogpu_default_local_map_params(C.byref(p))
     for k, v in over.items():
         setattr(p, k, v)
     return p
@@ -246,6 +274,28 @@ class LioGpu:
         st = self._check(self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
                                                          C.c_float(leaf), C.byref(n_map), None, 16, 0))
         return n_map.value, st
+
+    def publish_local_map(self, ids, poses, pose_now, params: "LocalMapParams | None" = None, **over):
+        """publishLocalMap (mapOptmization.cpp:2442-2541) -> (cloud (n,4), info dict, status)."""
+        prm = params if params is not None else local_map_params(**over)
+        ids = np.ascontiguousarray(ids, np.int32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        assert poses.shape[0] == ids.shape[0]
+        pose_now = np.ascontiguousarray(pose_now, np.float32)
+        info = LocalMapInfo()
+        n_out = C.c_int(0)
+        out = np.empty((1, 4), np.float32)
+        st = self.lib.liogpu_publish_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                               pose_now.ctypes.data, C.byref(prm), out.ctypes.data, 16, out.shape[0],
+                                               C.byref(n_out), C.byref(info))
+        if st == E_CAPACITY:  # retry with the reported size
+            out = np.empty((n_out.value, 4), np.float32)
+            st = self.lib.liogpu_publish_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                                   pose_now.ctypes.data, C.byref(prm), out.ctypes.data, 16,
+                                                   out.shape[0], C.byref(n_out), C.byref(info))
+        self._check(st)
+        d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "reserved"}
+        return out[: n_out.value].copy(), d, st
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

@@ -55,6 +55,14 @@ struct Index {
     const size_t found = tree->knnSearch(qq, 6, idx, d2);
     for (size_t k = 0; k < found; ++k) { r.d2[k] = d2[k]; r.idx[k] = idx[k]; }
   }
+  void knn_dist(const P4& q, KnnDist& r) const {
+    r.init();
+    int idx[32]; float d2[32];
+    const float qq[3] = {q.x, q.y, q.z};
+    const size_t found = tree->knnSearch(qq, (size_t)r.k, idx, d2);
+    for (size_t k = 0; k < found; ++k) r.d2[k] = d2[k];
+    r.found = (int)found;
+  }
 };
 #else
 struct Index {
@@ -62,6 +70,7 @@ struct Index {
   const P4* pts; int n;
   void build(const P4* p, int count) { pts = p; n = count; tree.build(p, count); }
   void knn(const P4& q, Knn6& r) const { tree.knn(q, r); }
+  void knn_dist(const P4& q, KnnDist& r) const { tree.knn(q, r); }
 };
 #endif
 
@@ -152,6 +161,68 @@ int SYM(build_local_map)(const float* clouds4, const int* offsets, const float* 
                          (float*)(raw.data() + offsets[f]), threads);
   return SYM(voxel_grid)((const float*)raw.data(), total, leaf, out4, n_out);
 }
+
+// f2: publishLocalMap (MO:2442-2541).  clouds4/offsets/pose6s = the keyframes to publish (the caller passes the
+// last localMapKeyFramesNumber, MO:2462) and their poses; pose_now6 = transformTobeMapped.  brute != 0: the
+// outlier filter's (meanK+1)-NN by exhaustive search, else through the KD-tree (the reference's path).
+// out4 must hold offsets[k] points.  md_out (optional, n_cropped floats) receives the per-point mean distances.
+// Returns 1 when the VoxelGrid overflow guard fired.
+int SYM(publish_local_map)(const float* clouds4, const int* offsets, const float* pose6s, int k, const float* pose_now6,
+                           const LocalMapParams* prm, int brute, float* out4, int* n_out, LocalMapInfo* info,
+                           float* md_out, int threads) {
+  std::memset(info, 0, sizeof(*info));
+  *n_out = 0;
+  if (k <= 0) return 0;  // cloudKeyPoses3D->points.empty(), MO:2444
+  const int total = offsets[k];
+  std::vector<P4> globalMapCloud((size_t)total);
+  for (int f = 0; f < k; ++f)   // MO:2463-2466
+    SYM(transform_cloud)(clouds4 + 4 * (size_t)offsets[f], offsets[f + 1] - offsets[f], pose6s + 6 * f,
+                         (float*)(globalMapCloud.data() + offsets[f]), threads);
+  float m[12];
+  yaw_frame_T(pose_now6, m);
+  std::vector<P4> transformedGlobalMapCloud((size_t)total);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int i = 0; i < total; ++i) transformedGlobalMapCloud[i] = pcl_transform_se3(m, globalMapCloud[i]);
+  std::vector<P4> tempCloud;
+  pass_through_xy(transformedGlobalMapCloud, -prm->left, prm->right, -prm->back, prm->front, tempCloud);
+  info->n_concat = total;
+  info->n_cropped = (int)tempCloud.size();
+  info->n_after_sor = info->n_cropped;
+  if (prm->use_removing_outliers && !tempCloud.empty()) {   // MO:2510-2516
+    const int n = (int)tempCloud.size();
+    const P4* pts = tempCloud.data();
+    std::vector<float> distances;
+    int valid;
+    if (brute) {
+      valid = sor_mean_distances(n, prm->mean_k, [&](int i, KnnDist& r) {
+        for (int j = 0; j < n; ++j) r.insert(l2_simple(pts[i], pts[j]), j);
+      }, distances, threads);
+    } else {
+      Index ix;
+      ix.build(pts, n);
+      valid = sor_mean_distances(n, prm->mean_k, [&](int i, KnnDist& r) { ix.knn_dist(pts[i], r); }, distances, threads);
+    }
+    if (md_out) std::memcpy(md_out, distances.data(), (size_t)n * sizeof(float));
+    std::vector<int> kept;
+    sor_select(distances, valid, (double)prm->stddev_threshold, kept, info->sor_mean, info->sor_stddev, info->sor_threshold);
+    std::vector<P4> filtered(kept.size());
+    for (size_t i = 0; i < kept.size(); ++i) filtered[i] = tempCloud[kept[i]];
+    tempCloud.swap(filtered);
+    info->n_after_sor = (int)tempCloud.size();
+  }
+  int ov = 0;
+  if (prm->use_down_sampling && !tempCloud.empty()) {   // MO:2517-2540
+    std::vector<P4> ds;
+    ov = voxel_grid(tempCloud.data(), (int)tempCloud.size(), prm->leaf, ds);
+    tempCloud.swap(ds);
+  }
+  info->leaf_overflow = ov;
+  info->n_out = (int)tempCloud.size();
+  std::memcpy(out4, tempCloud.data(), tempCloud.size() * sizeof(P4));
+  *n_out = (int)tempCloud.size();
+  return ov;
+}
+void SYM(yaw_frame_T)(const float* pose_now6, float* m12) { yaw_frame_T(pose_now6, m12); }
 
 // KD-tree handle (kdtreeSurfFromMap->setInputCloud, MO:1846).  The map memory must outlive the handle.
 void* SYM(index_build)(const float* map4, int nm) {

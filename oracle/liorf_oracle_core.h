@@ -141,6 +141,28 @@ struct Knn6 {
   inline bool tie() const {
     return d2[0] == d2[1] || d2[1] == d2[2] || d2[2] == d2[3] || d2[3] == d2[4] || d2[4] == d2[5];
   }
+  inline float worst() const { return d2[5]; }
+};
+
+// The k smallest L2_Simple distances only (ascending) — what pcl::StatisticalOutlierRemoval reads from
+// nearestKSearch(index, meanK + 1, ...) (f2, MO:2513-2514).  Equidistant neighbours carry equal values, so no
+// tie rule is involved.
+struct KnnDist {
+  int k = 0;        // capacity, <= 32
+  int found = 0;    // min(k, points inserted)
+  float d2[32];
+  inline void init() {
+    found = 0;
+    for (int j = 0; j < 32; ++j) d2[j] = FLT_MAX;
+  }
+  inline float worst() const { return d2[k - 1]; }
+  inline void insert(float d, int /*id*/) {
+    if (found < k) ++found;
+    if (!(d < d2[k - 1])) return;
+    int j = k - 1;
+    while (j > 0 && d < d2[j - 1]) { d2[j] = d2[j - 1]; --j; }
+    d2[j] = d;
+  }
 };
 
 inline float l2_simple(const P4& q, const P4& p) {
@@ -217,7 +239,8 @@ struct KdTree {
     nodes[id].cut_lo = lmax; nodes[id].cut_hi = rmin;
     return id;
   }
-  void search_rec(int id, const P4& q, Knn6& r, double mind2, double off[3]) const {
+  template <class R>
+  void search_rec(int id, const P4& q, R& r, double mind2, double off[3]) const {
     const Node& nd = nodes[id];
     if (nd.left < 0) {
       for (int i = nd.lo; i < nd.hi; ++i) r.insert(l2_simple(q, reord[i]), perm[i]);
@@ -233,13 +256,14 @@ struct KdTree {
     search_rec(best, q, r, mind2, off);
     const double save = off[d];
     const double m2 = mind2 + cut - save;
-    if (m2 * 0.999999 <= (double)r.d2[5]) {
+    if (m2 * 0.999999 <= (double)r.worst()) {
       off[d] = cut;
       search_rec(other, q, r, m2, off);
       off[d] = save;
     }
   }
-  void knn(const P4& q, Knn6& r) const {
+  template <class R>
+  void knn(const P4& q, R& r) const {
     r.init();
     if (n == 0) return;
     double off[3], mind2 = 0;
@@ -628,6 +652,123 @@ inline bool lm_solve_update(const double JtJ[36], const double Jtr[6], int iterC
   const float tx = X[3] * 100, ty = X[4] * 100, tz = X[5] * 100;
   deltaT = (float)std::sqrt((double)tx * tx + (double)ty * ty + (double)tz * tz);
   return (double)deltaR < 0.05 && (double)deltaT < 0.05;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f2: mapOptimization::publishLocalMap (MO:2442-2541) — runs after every registration (MO:504).
+// Third-party arithmetic restated here ([3P], versions unpinned like everything else in this file):
+//   * Eigen::AngleAxisf(-yaw, UnitZ) -> toRotationMatrix (Eigen 3.3 AngleAxis.h): diagonal
+//     cos1_axis .* axis + c, so zz = (1 - c) * 1 * 1 + c; Affine3f::rotate multiplies the (identity)
+//     linear part on the right, which changes no value.
+//   * pcl::transformPointCloud(in, out, Affine3f) (PCL 1.10 common/impl/transforms.hpp,
+//     detail::Transformer<float>::se3, SSE form): per coordinate x*c0 + (y*c1 + (z*c2 + c3)).
+//   * pcl::PassThrough (filters/impl/passthrough.hpp): drops non-finite points, keeps min <= v <= max,
+//     input order.
+//   * pcl::StatisticalOutlierRemoval::applyFilterIndices (filters/impl/statistical_outlier_removal.hpp).
+struct LocalMapParams {   // utility.h:219-229
+  float left, right, front, back;
+  int use_removing_outliers, mean_k;
+  float stddev_threshold;
+  int use_down_sampling;
+  float leaf;
+};
+struct LocalMapInfo {
+  int n_concat, n_cropped, n_after_sor, n_out, leaf_overflow, pad;
+  double sor_mean, sor_stddev, sor_threshold;
+};
+
+// transformMatrix of MO:2474-2488 as a row-major 3x4; pose_now = transformTobeMapped (MO:2249-2254).
+// `cos(-thisPoseYaw)` resolves to the float overload (utility.h:61 `using namespace std`), so every
+// operation is f32; canonical trig as in pose_to_T.
+inline void yaw_frame_T(const float pose_now[6], float m[12]) {
+  const float yaw = pose_now[2], X = pose_now[3], Y = pose_now[4], Z = pose_now[5];
+  const float nyaw = -yaw;
+  const float c = (float)std::cos((double)nyaw), s = (float)std::sin((double)nyaw);
+  const float transformedX = X * c - Y * s;   // MO:2474
+  const float transformedY = Y * c + X * s;   // MO:2475
+  const float transformedZ = Z;               // MO:2476
+  // AngleAxisf(angle = -yaw, axis = (0,0,1)).toRotationMatrix()
+  const float ax = 0.f, ay = 0.f, az = 1.f;
+  const float sx = s * ax, sy = s * ay, sz = s * az;
+  const float c1x = (1.0f - c) * ax, c1y = (1.0f - c) * ay, c1z = (1.0f - c) * az;
+  float R[9];
+  float tmp = c1x * ay; R[1] = tmp - sz; R[3] = tmp + sz;
+  tmp = c1x * az;       R[2] = tmp + sy; R[6] = tmp - sy;
+  tmp = c1y * az;       R[5] = tmp - sx; R[7] = tmp + sx;
+  R[0] = c1x * ax + c; R[4] = c1y * ay + c; R[8] = c1z * az + c;
+  // Identity.linear() * R, row by row (Eigen coefficient-based 3x3 product, summed left to right)
+  const float I[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m[4 * i + j] = I[3 * i] * R[j] + I[3 * i + 1] * R[3 + j] + I[3 * i + 2] * R[6 + j];
+  m[3] = -transformedX; m[7] = -transformedY; m[11] = -transformedZ;   // MO:2487
+}
+
+inline P4 pcl_transform_se3(const float m[12], const P4& p) {   // MO:2489
+  P4 o;
+  o.x = p.x * m[0] + (p.y * m[1] + (p.z * m[2] + m[3]));
+  o.y = p.x * m[4] + (p.y * m[5] + (p.z * m[6] + m[7]));
+  o.z = p.x * m[8] + (p.y * m[9] + (p.z * m[10] + m[11]));
+  o.i = p.i;
+  return o;
+}
+
+// PassThrough on x then on y (MO:296-302, 2502-2506)
+inline void pass_through_xy(const std::vector<P4>& in, float xmin, float xmax, float ymin, float ymax, std::vector<P4>& out) {
+  std::vector<P4> fx;
+  for (const P4& p : in) {
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    if (p.x < xmin || p.x > xmax) continue;
+    fx.push_back(p);
+  }
+  out.clear();
+  for (const P4& p : fx) {
+    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+    if (p.y < ymin || p.y > ymax) continue;
+    out.push_back(p);
+  }
+}
+
+// Second half of StatisticalOutlierRemoval::applyFilterIndices: statistics of the per-point mean distances
+// (sequential f64 sums of f32 values / f32 squares), threshold, and the kept indices in input order.
+inline void sor_select(const std::vector<float>& distances, int valid_distances, double std_mul, std::vector<int>& kept,
+                       double& mean, double& stddev, double& threshold) {
+  double sum = 0, sq_sum = 0;
+  for (const float& distance : distances) {
+    sum += distance;
+    sq_sum += distance * distance;
+  }
+  mean = sum / static_cast<double>(valid_distances);
+  const double variance = (sq_sum - sum * sum / static_cast<double>(valid_distances)) / (static_cast<double>(valid_distances) - 1);
+  stddev = std::sqrt(variance);
+  threshold = mean + std_mul * stddev;
+  kept.clear();
+  for (int i = 0; i < (int)distances.size(); ++i) {
+    if (distances[i] > threshold) continue;   // negative_ == false
+    kept.push_back(i);
+  }
+}
+
+// First half: distances[i] = (float)( sum_{k=1..meanK} sqrt(nn_dists[k]) / meanK ), the sum in f64 over the f32
+// square roots of the ascending squared distances; nn_dists[0] is the query itself.  `knn(i, KnnDist&)` is the
+// exact (meanK+1)-NN provider (brute force or a KD-tree).  A search that returns fewer than meanK+1 points
+// (cloud too small) yields distance 0 and is not counted as valid.
+template <class KnnFn>
+inline int sor_mean_distances(int n, int mean_k, KnnFn knn, std::vector<float>& distances, int threads) {
+  distances.assign(n, 0.f);
+  int valid = 0;
+#pragma omp parallel for num_threads(threads) schedule(static) reduction(+ : valid)
+  for (int i = 0; i < n; ++i) {
+    KnnDist r;
+    r.k = mean_k + 1;
+    r.init();
+    knn(i, r);
+    if (r.found != mean_k + 1) { distances[i] = 0.f; continue; }
+    double dist_sum = 0.0;
+    for (int k = 1; k < mean_k + 1; ++k) dist_sum += std::sqrt(r.d2[k]);   // float sqrt
+    distances[i] = static_cast<float>(dist_sum / mean_k);
+    ++valid;
+  }
+  return valid;
 }
 
 }  // namespace liorf_oracle

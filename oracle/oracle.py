@@ -27,6 +27,18 @@ class DeskewParams(C.Structure):
                 ("max_range", C.c_float), ("max_intensity", C.c_float)]
 
 
+class LocalMapParams(C.Structure):
+    _fields_ = [("left", C.c_float), ("right", C.c_float), ("front", C.c_float), ("back", C.c_float),
+                ("use_removing_outliers", C.c_int), ("mean_k", C.c_int), ("stddev_threshold", C.c_float),
+                ("use_down_sampling", C.c_int), ("leaf", C.c_float)]
+
+
+class LocalMapInfo(C.Structure):
+    _fields_ = [("n_concat", C.c_int), ("n_cropped", C.c_int), ("n_after_sor", C.c_int), ("n_out", C.c_int),
+                ("leaf_overflow", C.c_int), ("pad", C.c_int), ("sor_mean", C.c_double), ("sor_stddev", C.c_double),
+                ("sor_threshold", C.c_double)]
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
     if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")):
@@ -115,6 +127,35 @@ class Oracle:
                                         C.c_int(len(clouds)), C.c_float(leaf), _p(out, C.c_float),
                                         C.byref(n_out), C.c_int(threads))
         return out[: n_out.value].copy(), bool(ov)
+
+    # -- f2 -------------------------------------------------------------------------------------
+    def yaw_frame_T(self, pose_now):
+        pose_now = np.ascontiguousarray(pose_now, dtype=np.float32)
+        m = np.zeros(12, np.float32)
+        self._f("yaw_frame_T")(_p(pose_now, C.c_float), _p(m, C.c_float))
+        return m
+
+    def publish_local_map(self, clouds, poses, pose_now, left=40.0, right=40.0, front=70.0, back=20.0,
+                          use_removing_outliers=True, mean_k=10, stddev_threshold=1.0, use_down_sampling=True,
+                          leaf=0.01, brute=False, threads: int = 1):
+        """publishLocalMap (MO:2442-2541) -> (cloud, info dict, mean distances of the cropped cloud)."""
+        offs = np.zeros(len(clouds) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([c.shape[0] for c in clouds])
+        cat = _f4(np.concatenate(clouds)) if clouds else np.zeros((0, 4), np.float32)
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 6)
+        pose_now = np.ascontiguousarray(pose_now, dtype=np.float32)
+        prm = LocalMapParams(left, right, front, back, int(use_removing_outliers), int(mean_k), stddev_threshold,
+                             int(use_down_sampling), leaf)
+        out = np.empty((max(cat.shape[0], 1), 4), np.float32)
+        md = np.zeros(max(cat.shape[0], 1), np.float32)
+        n_out = C.c_int(0)
+        info = LocalMapInfo()
+        self._f("publish_local_map")(_p(cat, C.c_float), _p(offs, C.c_int), _p(poses, C.c_float), C.c_int(len(clouds)),
+                                     _p(pose_now, C.c_float), C.byref(prm), C.c_int(1 if brute else 0),
+                                     _p(out, C.c_float), C.byref(n_out), C.byref(info), _p(md, C.c_float),
+                                     C.c_int(threads))
+        d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "pad"}
+        return out[: n_out.value].copy(), d, md[: info.n_cropped].copy()
 
     # -- a5 / a7 --------------------------------------------------------------------------------
     def index_build(self, map4):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-stage timings of the path outside the LM loop: deskew (config 2), sweep VoxelGrid,
-local-map rebuild = transform + concatenate + VoxelGrid + grid index (config 4 sizes), index build alone.
+local-map rebuild = transform + concatenate + VoxelGrid + grid index (config 4 sizes), publishLocalMap (§8 f2),
+index build alone.
 GPU device time (CUDA events inside the library) and wall time through the C ABI from host buffers, with the
 CPU oracle timed beside each stage.  Prints one JSON line per stage; results are checked bit-exact first."""
 import json
@@ -90,6 +91,31 @@ def main():
         assert np.array_equal(cat.view(np.uint32), want.view(np.uint32))
         res.append(dict(stage=f"config 4 tiled {tiles} ways: VoxelGrid per tile (device ms, max over tiles = N-GPU critical path)",
                         n_in=total, tiles=tiles, gpu_device_ms_max=max(per), gpu_device_ms_sum=sum(per), bit_equal=True))
+    # ---- publishLocalMap (every scan): 50 keyframes (6t.yaml) of voxelised 32-beam sweeps
+    g.keyframe_clear()
+    kf, kposes = [], []
+    for k in range(50):
+        p = synth.path_pose(0.5 * k)
+        ds, _ = o.voxel_grid(synth.to_packed(synth.make_scan(world, p, 32, seed=700 + k, cols=900)), 0.4)
+        kf.append(ds); kposes.append(p.astype(np.float32))
+    kposes = np.array(kposes)
+    for k, c in enumerate(kf):
+        g.keyframe_put(k, c)
+    now = kposes[-1]
+    for label, okw, gkw in (
+            ("utility.h defaults: outlier filter meanK 10 + leaf 0.01 (overflow guard)", dict(), dict()),
+            ("outlier filter meanK 10 + VoxelGrid leaf 0.2", dict(leaf=0.2), dict(local_mapping_surf_leaf_size=0.2)),
+            ("jeep.yaml: no outlier filter, VoxelGrid leaf 0.2", dict(leaf=0.2, use_removing_outliers=False),
+             dict(local_mapping_surf_leaf_size=0.2, use_removing_outliers=0))):
+        cpu1_ms, (want, winfo, _) = timeit(lambda: o.publish_local_map(kf, kposes, now, threads=1, **okw), reps=2, warm=1)
+        cpuN_ms, _ = timeit(lambda: o.publish_local_map(kf, kposes, now, threads=os.cpu_count(), **okw), reps=2, warm=1)
+        wall_ms, (got, info, _) = timeit(lambda: g.publish_local_map(ids, kposes, now, **gkw))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        res.append(dict(stage="publishLocalMap, 50 keyframes: " + label, n_in=info["n_concat"], n_cropped=info["n_cropped"],
+                        n_after_sor=info["n_after_sor"], n_out=info["n_out"], gpu_device_ms=info["gpu_ms"],
+                        gpu_wall_ms=wall_ms, cpu_ms=cpu1_ms, cpu_threads=1, cpu_ms_all_threads=cpuN_ms,
+                        cpu_threads_all=os.cpu_count(), bit_equal=True,
+                        algorithmic_bytes=16 * info["n_concat"] + 16 * info["n_out"]))
     # ---- index build alone (kdtreeSurfFromMap->setInputCloud), 500k-point map
     map4 = synth.make_local_map(world, 128, 500000, 0.2, seed=3, s0=-0.5)
     cpu_ms, h = timeit(lambda: o.index_build(map4), reps=3, warm=1)
