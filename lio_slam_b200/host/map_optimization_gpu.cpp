@@ -21,6 +21,7 @@ int ImageProjection::projectPointCloud() {
 mapOptimization::mapOptimization(const liogpu_params& params) : params_(params) {
   const int st = liogpu_create(&ctx_, &params_);  // allocateMemory (mapOptmization.cpp:316-349)
   if (st != LIOGPU_OK) throw std::runtime_error("liogpu_create failed (no sm_100 GPU? there is no CPU fallback)");
+  liogpu_default_local_map_params(&localMapParams);  // utility.h:219-229
 }
 mapOptimization::~mapOptimization() { liogpu_destroy(ctx_); }
 const char* mapOptimization::lastError() const { return liogpu_last_error(ctx_); }
@@ -186,6 +187,32 @@ void mapOptimization::saveKeyFrame() {  // :2128-2142 without the factor graph
                                    sizeof(PointType));
   cloudKeyPoses3D.push_back(p3);
   cloudKeyPoses6D.push_back(p6);
+}
+
+void mapOptimization::publishLocalMap() {  // :2442-2541; the reference calls it after every registration (:504)
+  if (cloudKeyPoses3D.empty()) return;     // :2444
+  const int thisPoseNum = (int)cloudKeyPoses3D.size();
+  const int startPoseNum = (thisPoseNum < localMapKeyFramesNumber) ? 0 : thisPoseNum - localMapKeyFramesNumber;  // :2462
+  std::vector<int> ids;
+  std::vector<float> poses;
+  for (int i = startPoseNum; i < thisPoseNum; ++i) {
+    const PointTypePose& p = cloudKeyPoses6D[i];
+    const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+    ids.push_back(i);
+    poses.insert(poses.end(), pose6, pose6 + 6);
+  }
+  // thisPoseX/Y/Z/Yaw are copies of transformTobeMapped (:2249-2254)
+  int n = 0;
+  localMapCloud.resize(localMapCloud.capacity() > 0 ? localMapCloud.capacity() : 1);
+  int st = liogpu_publish_local_map(ctx_, ids.data(), poses.data(), (int)ids.size(), transformTobeMapped, &localMapParams,
+                                    localMapCloud.data(), sizeof(PointType), (int)localMapCloud.size(), &n, &lastLocalMapInfo);
+  if (st == LIOGPU_E_CAPACITY) {
+    localMapCloud.resize(n);
+    st = liogpu_publish_local_map(ctx_, ids.data(), poses.data(), (int)ids.size(), transformTobeMapped, &localMapParams,
+                                  localMapCloud.data(), sizeof(PointType), n, &n, &lastLocalMapInfo);
+  }
+  lastStatus = st;
+  localMapCloud.resize(st < 0 ? 0 : n);
 }
 
 }  // namespace liorf_gpu

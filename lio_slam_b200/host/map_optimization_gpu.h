@@ -78,6 +78,11 @@ class mapOptimization {
   float surroundingKeyframeSearchRadius = 50.0f, surroundingKeyframeDensity = 2.0f;
   float surroundingkeyframeAddingDistThreshold = 1.0f, surroundingkeyframeAddingAngleThreshold = 0.2f;
   bool fetchLocalMap = false;      // copy laserCloudSurfFromMapDS back (it is only needed for publishing)
+  // publishLocalMap settings (utility.h:219-229) and its output cloud (tempCloud, :2541)
+  int localMapKeyFramesNumber = 30;
+  liogpu_local_map_params localMapParams;
+  liogpu_local_map_info lastLocalMapInfo{};
+  Cloud localMapCloud;
   liogpu_s2m_info lastInfo{};
   int lastStatus = 0;
 
@@ -91,6 +96,7 @@ class mapOptimization {
   Cloud transformPointCloud(const Cloud& in, const PointTypePose& pose);  // :849-868 -> liogpu_transform_cloud
   bool saveFrame() const;                                // :1909-1928 (host)
   void saveKeyFrame();                                   // the cloud/pose bookkeeping of saveKeyFramesAndFactor (:2128-2142)
+  void publishLocalMap();                                // :2442-2541 -> liogpu_publish_local_map (fills localMapCloud)
   const char* lastError() const;
   liogpu_ctx* context() { return ctx_; }
 

@@ -18,7 +18,7 @@ using namespace liorf_gpu;
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s sequence.bin poses.txt [device] [scan_leaf] [map_leaf]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s sequence.bin poses.txt [device] [scan_leaf] [map_leaf] [publish_local_map 0|1]\n", argv[0]);
     return 2;
   }
   liogpu_params prm;
@@ -34,8 +34,13 @@ int main(int argc, char** argv) {
   if (std::fread(&n_scans, 4, 1, f) != 1) return 2;
   try {
     mapOptimization MO(prm);
-    double gpu_ms = 0, wall_ms = 0;
-    int registered = 0;
+    double gpu_ms = 0, wall_ms = 0, lmap_ms = 0;
+    int registered = 0, published = 0;
+    const bool publish = argc > 6 && std::atoi(argv[6]) != 0;  // also run publishLocalMap after every scan (:504)
+    if (publish) {
+      MO.localMapKeyFramesNumber = 50;                            // 6t.yaml:17
+      MO.localMapParams.local_mapping_surf_leaf_size = 0.2f;      // jeep.yaml:23
+    }
     for (int s = 0; s < n_scans; ++s) {
       double t;
       float guess[6];
@@ -51,13 +56,21 @@ int main(int argc, char** argv) {
       if (MO.lastStatus < 0) { std::fprintf(stderr, "scan %d: %s\n", s, MO.lastError()); return 1; }
       if (!MO.cloudKeyPoses3D.empty()) { gpu_ms += MO.lastInfo.gpu_ms; ++registered; }
       if (MO.saveFrame()) MO.saveKeyFrame();
+      if (publish) {
+        MO.publishLocalMap();
+        if (MO.lastStatus < 0) { std::fprintf(stderr, "scan %d publishLocalMap: %s\n", s, MO.lastError()); return 1; }
+        lmap_ms += MO.lastLocalMapInfo.gpu_ms;
+        ++published;
+      }
       wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       std::fprintf(out, "%d %.9g %.9g %.9g %.9g %.9g %.9g %d %d %d %d\n", s, MO.transformTobeMapped[0], MO.transformTobeMapped[1],
                    MO.transformTobeMapped[2], MO.transformTobeMapped[3], MO.transformTobeMapped[4], MO.transformTobeMapped[5],
                    MO.lastInfo.iterations, MO.lastInfo.n_sel, (int)MO.cloudKeyPoses3D.size(), MO.laserCloudSurfFromMapDSNum);
     }
-    std::printf("{\"scans\": %d, \"registered\": %d, \"keyframes\": %d, \"wall_ms_per_scan\": %.4f, \"loop_gpu_ms_per_scan\": %.4f}\n",
-                n_scans, registered, (int)MO.cloudKeyPoses3D.size(), wall_ms / n_scans, registered ? gpu_ms / registered : 0.0);
+    std::printf("{\"scans\": %d, \"registered\": %d, \"keyframes\": %d, \"wall_ms_per_scan\": %.4f, \"loop_gpu_ms_per_scan\": %.4f, "
+                "\"local_map_gpu_ms_per_scan\": %.4f, \"local_map_points\": %d}\n",
+                n_scans, registered, (int)MO.cloudKeyPoses3D.size(), wall_ms / n_scans, registered ? gpu_ms / registered : 0.0,
+                published ? lmap_ms / published : 0.0, (int)MO.localMapCloud.size());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());
     return 1;

@@ -392,6 +392,12 @@ def test_replay_driver_tracks_ground_truth(world, tmp_path):
     assert np.abs(poses[:, 3:] - gts[:, 3:]).max() < 0.08 and np.abs(poses[:, :3] - gts[:, :3]).max() < 0.01
     assert (rows[1:, 7] >= 1).all() and (rows[1:, 8] > 500).all()
     print(summary)
+    # the same replay with publishLocalMap after every scan (mapOptmization.cpp:504): poses unchanged, a cloud published
+    out2 = str(tmp_path / "poses2.txt")
+    r = subprocess.run([exe, seq, out2, "0", "0.4", "0.5", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    s2 = json.loads(r.stdout.strip().splitlines()[-1])
+    assert np.array_equal(np.loadtxt(out2), rows) and s2["local_map_points"] > 1000 and s2["local_map_gpu_ms_per_scan"] > 0
 
 
 def test_device_resident_pipeline_config2(oracle, world):
