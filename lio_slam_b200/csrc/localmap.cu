@@ -273,9 +273,8 @@ sor_left_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ 
 
 // block per isolated point: every point of the cloud is inspected once (coalesced), the per-thread lists are merged
 // per warp and then across the warps.
-constexpr int BR_THREADS = 512;
 constexpr int BR_BATCH = 8;  // independent loads in flight per thread
-template <int K>
+template <int K, int BR_THREADS>
 __global__ void __launch_bounds__(BR_THREADS)
 sor_brute_kernel(const float4* __restrict__ sorted, const GridParams* __restrict__ gp, int mean_k, float* __restrict__ md,
                  const uint32_t* __restrict__ brute_list, const uint32_t* __restrict__ brute_count) {
@@ -389,7 +388,8 @@ cudaError_t launch_sor_knn(Ctx* c, const float4* sorted, const uint32_t* cs, con
                                                                                   left_list, left_count);
   sor_left_kernel<K><<<c->sm_count * 2, 256, 0, c->stream>>>(sorted, cs, d_gp, mean_k, md, left_list, left_count,
                                                              brute_list, brute_count);
-  sor_brute_kernel<K><<<c->sm_count, BR_THREADS, 0, c->stream>>>(sorted, d_gp, mean_k, md, brute_list, brute_count);
+  constexpr int BR_THREADS = K <= 16 ? 1024 : 512;  // register budget of the K-entry private lists
+  sor_brute_kernel<K, BR_THREADS><<<c->sm_count, BR_THREADS, 0, c->stream>>>(sorted, d_gp, mean_k, md, brute_list, brute_count);
   c->launches += 3;
   return cudaGetLastError();
 }
