@@ -189,6 +189,14 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
                              void* xyzi_out, int out_stride, int cap_out, int* n_out,
                              liogpu_local_map_info* info);
 
+/* The keyframe-merging loops outside the registration: saveMapService (MO:936-950: every keyframe, optional
+ * VoxelGrid at req.resolution), publishGlobalMap (MO:1031-1039: the key poses chosen by the host, VoxelGrid at
+ * globalMapVisualizationLeafSize) and loopFindNearKeyframes (MO:1360-1383).  Transforms the k named keyframes by
+ * their poses, concatenates them in the given order and, when leaf > 0, applies pcl::VoxelGrid.  Unlike
+ * liogpu_build_local_map it leaves the registration's local map and index untouched. */
+int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k, float leaf,
+                           void* xyzi_out, int out_stride, int cap_out, int* n_out);
+
 /* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);

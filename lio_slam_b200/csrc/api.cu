@@ -80,6 +80,52 @@ void clobber(Ctx* c, DevBuf* buf) {
   if (c->resident == buf) { c->resident = nullptr; c->resident_n = 0; }
 }
 
+// The k named keyframes as device tables for the multi-keyframe transform kernels: validates the ids, stages
+// poses [k*6 f32] | offsets [k+1 i32] | source pointers [k u64] in pinned memory (second half of h_pinned) and
+// uploads them in one copy.  Concatenation order = argument order (the reference's "+=" loops).
+struct KfTables {
+  const float4* const* srcs;
+  const int* offs;
+  const float* poses;
+  float* T12;
+  size_t total;
+};
+int stage_keyframes(Ctx* c, const char* who, const int* ids, const float* pose6s, int k, KfTables& t) {
+  t.total = 0;
+  for (int f = 0; f < k; ++f) {
+    auto it = c->keyframes.find(ids[f]);
+    if (it == c->keyframes.end()) { c->err = std::string(who) + ": unknown keyframe id"; return LIOGPU_E_NO_KEYFRAME; }
+    t.total += (size_t)it->second.second;
+  }
+  if (t.total > 0x7fffffffULL) { c->err = std::string(who) + ": cloud too large"; return LIOGPU_E_INVALID; }
+  if ((size_t)k * 6 * sizeof(float) > 32768) {
+    c->err = std::string(who) + ": too many keyframes in one call (max 1365)";
+    return LIOGPU_E_INVALID;
+  }
+  if (t.total == 0) return LIOGPU_OK;
+  char* hp = (char*)c->h_pinned + 131072;
+  float* hposes = reinterpret_cast<float*>(hp);
+  int* hoffs = reinterpret_cast<int*>(hp + 32768);
+  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
+  std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
+  size_t off = 0;
+  for (int f = 0; f < k; ++f) {
+    auto& kf = c->keyframes[ids[f]];
+    hoffs[f] = (int)off;
+    hsrcs[f] = kf.first.as<float4>();
+    off += (size_t)kf.second;
+  }
+  hoffs[k] = (int)off;
+  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));  // scratch: tables + k transforms
+  char* dp = (char*)c->dbg_d2.p;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
+  t.srcs = reinterpret_cast<const float4* const*>(dp + 49152);
+  t.offs = reinterpret_cast<const int*>(dp + 32768);
+  t.poses = reinterpret_cast<const float*>(dp);
+  t.T12 = reinterpret_cast<float*>(dp + 65536);
+  return LIOGPU_OK;
+}
+
 int enter(liogpu_ctx* ctx) {
   if (!ctx) return LIOGPU_E_INVALID;
   ctx->c.err.clear();
@@ -327,43 +373,17 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   Ctx* c = &ctx->c;
   if (k < 0 || (k > 0 && (!ids || !pose6s)) || !n_map) { c->err = "liogpu_build_local_map: bad arguments"; return LIOGPU_E_INVALID; }
   *n_map = 0;
-  size_t total = 0;
-  for (int f = 0; f < k; ++f) {
-    auto it = c->keyframes.find(ids[f]);
-    if (it == c->keyframes.end()) { c->err = "liogpu_build_local_map: unknown keyframe id"; return LIOGPU_E_NO_KEYFRAME; }
-    total += (size_t)it->second.second;
-  }
-  if (total > 0x7fffffffULL) { c->err = "local map too large"; return LIOGPU_E_INVALID; }
+  KfTables t;
+  rc = stage_keyframes(c, "liogpu_build_local_map", ids, pose6s, k, t);
+  if (rc) return rc;
+  const size_t total = t.total;
   c->grid_valid = false;
   c->n_map = 0;
   if (total == 0) return LIOGPU_W_NO_KEYFRAMES;
   LIOGPU_CUDA_OK(c, c->map_raw4.reserve(total * sizeof(float4)));
-  LIOGPU_CUDA_OK(c, c->misc.reserve(256));
-  if ((size_t)k * 6 * sizeof(float) > 32768) {
-    c->err = "too many keyframes in one local map (max 1365)";
-    return LIOGPU_E_INVALID;
-  }
-  // staging (pinned, second half of h_pinned): poses [k*6 f32] | offsets [k+1 i32] | source pointers [k u64]
-  char* hp = (char*)c->h_pinned + 131072;
-  float* hposes = reinterpret_cast<float*>(hp);
-  int* hoffs = reinterpret_cast<int*>(hp + 32768);
-  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
-  std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
-  size_t off = 0;
-  for (int f = 0; f < k; ++f) {  // transformPointCloud + "+=" concatenation order (mapOptmization.cpp:1566-1576)
-    auto& kf = c->keyframes[ids[f]];
-    hoffs[f] = (int)off;
-    hsrcs[f] = kf.first.as<float4>();
-    off += (size_t)kf.second;
-  }
-  hoffs[k] = (int)off;
-  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));  // scratch: tables + k transforms
-  char* dp = (char*)c->dbg_d2.p;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  LIOGPU_CUDA_OK(c, launch_transform_multi(c, reinterpret_cast<const float4* const*>(dp + 49152),
-                                           reinterpret_cast<const int*>(dp + 32768), k, reinterpret_cast<const float*>(dp),
-                                           reinterpret_cast<float*>(dp + 65536), (long long)total, c->map_raw4.as<float4>()));
+  // transformPointCloud + "+=" concatenation (mapOptmization.cpp:1566-1576) in one launch
+  LIOGPU_CUDA_OK(c, launch_transform_multi(c, t.srcs, t.offs, k, t.poses, t.T12, (long long)total, c->map_raw4.as<float4>()));
   int m = 0;
   bool overflow = false;
   rc = voxel_downsample_dev(c, c->map_raw4.as<float4>(), (int)total, leaf, c->map4, &m, &overflow);
@@ -419,35 +439,11 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
     return LIOGPU_E_INVALID;
   }
   if (k == 0) return LIOGPU_W_NO_KEYFRAMES;  // cloudKeyPoses3D->points.empty(), mapOptmization.cpp:2444
-  size_t total = 0;
-  for (int f = 0; f < k; ++f) {
-    auto it = c->keyframes.find(ids[f]);
-    if (it == c->keyframes.end()) { c->err = "liogpu_publish_local_map: unknown keyframe id"; return LIOGPU_E_NO_KEYFRAME; }
-    total += (size_t)it->second.second;
-  }
-  if (total > 0x7fffffffULL) { c->err = "local map too large"; return LIOGPU_E_INVALID; }
-  if ((size_t)k * 6 * sizeof(float) > 32768) {
-    c->err = "too many keyframes in one local map (max 1365)";
-    return LIOGPU_E_INVALID;
-  }
+  KfTables t;
+  rc = stage_keyframes(c, "liogpu_publish_local_map", ids, pose6s, k, t);   // "+=" order of mapOptmization.cpp:2463-2466
+  if (rc) return rc;
+  const size_t total = t.total;
   if (total == 0) return LIOGPU_OK;
-  // staging, same layout as liogpu_build_local_map
-  char* hp = (char*)c->h_pinned + 131072;
-  float* hposes = reinterpret_cast<float*>(hp);
-  int* hoffs = reinterpret_cast<int*>(hp + 32768);
-  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
-  std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
-  size_t off = 0;
-  for (int f = 0; f < k; ++f) {  // "+=" concatenation order (mapOptmization.cpp:2463-2466)
-    auto& kf = c->keyframes[ids[f]];
-    hoffs[f] = (int)off;
-    hsrcs[f] = kf.first.as<float4>();
-    off += (size_t)kf.second;
-  }
-  hoffs[k] = (int)off;
-  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));
-  char* dp = (char*)c->dbg_d2.p;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
   // The yaw-aligned vehicle frame (mapOptmization.cpp:2474-2488), f32 like the reference; canonical trig = f64
   // sin/cos rounded to f32 as everywhere in this library.  Rotation = Eigen::AngleAxisf(-yaw, UnitZ)
   // .toRotationMatrix(): its zz entry is (1 - c) + c, which is not always exactly 1.
@@ -471,9 +467,7 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   const float4* result = nullptr;
   int m = 0;
-  rc = publish_local_map_dev(c, reinterpret_cast<const float4* const*>(dp + 49152), reinterpret_cast<const int*>(dp + 32768),
-                             k, reinterpret_cast<const float*>(dp), reinterpret_cast<float*>(dp + 65536), (long long)total,
-                             yw, params, &result, &m, info);
+  rc = publish_local_map_dev(c, t.srcs, t.offs, k, t.poses, t.T12, (long long)total, yw, params, &result, &m, info);
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
@@ -486,6 +480,42 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
   info->gpu_ms = c->last_ms;
   return info->leaf_overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, void* xyzi_out,
+                           int out_stride, int cap_out, int* n_out) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (k < 0 || (k > 0 && (!ids || !pose6s)) || !n_out) { c->err = "liogpu_merge_keyframes: bad arguments"; return LIOGPU_E_INVALID; }
+  *n_out = 0;
+  KfTables t;
+  rc = stage_keyframes(c, "liogpu_merge_keyframes", ids, pose6s, k, t);
+  if (rc) return rc;
+  if (t.total == 0) return LIOGPU_OK;
+  const int total = (int)t.total;
+  // scratch of publishLocalMap: neither the registration's local map / index nor a resident sweep is touched
+  LIOGPU_CUDA_OK(c, c->lm_a.reserve(t.total * sizeof(float4)));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  LIOGPU_CUDA_OK(c, launch_transform_multi(c, t.srcs, t.offs, k, t.poses, t.T12, (long long)total, c->lm_a.as<float4>()));
+  const float4* result = c->lm_a.as<float4>();
+  int m = total;
+  bool overflow = false;
+  if (leaf > 0.f) {  // req.resolution != 0 (mapOptmization.cpp:943) / the visualisation leaf (:1037-1039)
+    rc = voxel_downsample_dev(c, result, total, leaf, c->lm_out, &m, &overflow);
+    if (rc) return rc;
+    result = c->lm_out.as<float4>();
+  }
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_out = m;
+  if (xyzi_out && m > 0) {
+    if (m > cap_out) { c->err = "liogpu_merge_keyframes: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, result, m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
 }
 
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {

@@ -76,16 +76,16 @@ vox_minmax_kernel(const float4* __restrict__ pts, int n, unsigned* __restrict__ 
   }
 }
 
-__global__ void vox_setup_kernel(const unsigned* __restrict__ mm, float leaf, VoxelSetup* __restrict__ s) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  VoxelSetup v;
-  v.n_valid = (int)mm[6];
+// A.1 steps 2-4 from the f32 bounding box and the finite count
+__device__ __forceinline__ void vox_setup_compute(const float mn[3], const float mx[3], int n_valid, float leaf,
+                                                  VoxelSetup& v) {
+  v.n_valid = n_valid;
   const float inv = 1.0f / leaf;
   v.inv_leaf = inv;
   long long d[3];
   for (int a = 0; a < 3; ++a) {
-    v.min_p[a] = ord2f(mm[a]);
-    v.max_p[a] = ord2f(mm[3 + a]);
+    v.min_p[a] = mn[a];
+    v.max_p[a] = mx[a];
     d[a] = (long long)((v.max_p[a] - v.min_p[a]) * inv) + 1;  // A.1 step 3
   }
   v.overflow = (v.n_valid > 0 && d[0] * d[1] * d[2] > 2147483647LL) ? 1 : 0;
@@ -98,6 +98,7 @@ __global__ void vox_setup_kernel(const unsigned* __restrict__ mm, float leaf, Vo
   v.mul2 = v.div_b[0] * v.div_b[1];
   v.n_cells = 0;
   v.key_bits = 0;
+  v.n_vox = 0;
   if (!v.overflow && v.n_valid > 0) {
     v.n_cells = (unsigned)v.div_b[0] * (unsigned)v.div_b[1] * (unsigned)v.div_b[2];
     // keys live in [0, n_cells]; n_cells itself marks non-finite points (sorted last, then dropped)
@@ -106,7 +107,23 @@ __global__ void vox_setup_kernel(const unsigned* __restrict__ mm, float leaf, Vo
     while (b < 32 && (maxkey >> b) != 0u) ++b;
     v.key_bits = b;
   }
+}
+
+__global__ void vox_setup_kernel(const unsigned* __restrict__ mm, float leaf, VoxelSetup* __restrict__ s) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  VoxelSetup v;
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a) { mn[a] = ord2f(mm[a]); mx[a] = ord2f(mm[3 + a]); }
+  vox_setup_compute(mn, mx, (int)mm[6], leaf, v);
   *s = v;
+}
+
+__device__ __forceinline__ uint32_t vox_key_of(const float4 p, const VoxelSetup& s) {
+  if (!finite3(p)) return s.n_cells;
+  const int ix = (int)(floorf(p.x * s.inv_leaf) - (float)s.min_b[0]);  // A.1 step 5
+  const int iy = (int)(floorf(p.y * s.inv_leaf) - (float)s.min_b[1]);
+  const int iz = (int)(floorf(p.z * s.inv_leaf) - (float)s.min_b[2]);
+  return (uint32_t)(ix + iy * s.mul1 + iz * s.mul2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -116,15 +133,7 @@ vox_key_kernel(const float4* __restrict__ pts, int n, const VoxelSetup* __restri
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float4 p = pts[i];
-  uint32_t key = s.n_cells;
-  if (finite3(p)) {
-    const int ix = (int)(floorf(p.x * s.inv_leaf) - (float)s.min_b[0]);  // A.1 step 5
-    const int iy = (int)(floorf(p.y * s.inv_leaf) - (float)s.min_b[1]);
-    const int iz = (int)(floorf(p.z * s.inv_leaf) - (float)s.min_b[2]);
-    key = (uint32_t)(ix + iy * s.mul1 + iz * s.mul2);
-  }
-  keys[i] = key;
+  keys[i] = vox_key_of(pts[i], s);
 }
 
 // head[i] = 1 at the first sorted position of every occupied voxel (finite points only), else 0
@@ -245,6 +254,125 @@ vox_centroid_long_kernel(const float4* __restrict__ pts, const uint32_t* __restr
   }
 }
 
+// ---- small clouds (the key-pose filter downSizeFilterSurroundingKeyPoses, MO:1535-1536, runs on a few hundred
+// poses every scan): the whole filter in ONE block — bounding box, keys, a shared-memory sort of (key, input
+// index) pairs (the index makes the order of equal keys the input order), head flags + scan, per-voxel sequential
+// sums.  Same arithmetic as the multi-kernel pipeline, one launch instead of twenty.
+constexpr int VS_MAX = 2048;
+constexpr int VS_THREADS = 1024;
+__global__ void __launch_bounds__(VS_THREADS)
+vox_small_kernel(const float4* __restrict__ pts, int n, float leaf, VoxelSetup* __restrict__ sp, float4* __restrict__ out) {
+  __shared__ unsigned long long comp[VS_MAX];
+  __shared__ uint32_t seg[VS_MAX + 1];
+  __shared__ float smn[VS_THREADS / 32][3], smx[VS_THREADS / 32][3];
+  __shared__ uint32_t swsum[VS_THREADS / 32];
+  __shared__ VoxelSetup s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // bounding box of the finite points
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  unsigned cnt = 0;
+  for (int i = tid; i < n; i += VS_THREADS) {
+    const float4 p = pts[i];
+    if (finite3(p)) {
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { smn[w][a] = mn[a]; smx[w][a] = mx[a]; }
+    swsum[w] = cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned total = 0;
+    for (int k = 0; k < VS_THREADS / 32; ++k) {
+      total += swsum[k];
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], smn[k][a]); mx[a] = fmaxf(mx[a], smx[k][a]); }
+    }
+    if (total == 0) {  // same encoding the ordered-uint path decodes for an all-non-finite cloud
+      for (int a = 0; a < 3; ++a) { mn[a] = ord2f(0xffffffffu); mx[a] = ord2f(0u); }
+    }
+    VoxelSetup v;
+    vox_setup_compute(mn, mx, (int)total, leaf, v);
+    s = v;
+  }
+  __syncthreads();
+  if (s.overflow || s.n_valid == 0) {
+    if (tid == 0) *sp = s;
+    return;
+  }
+  int m = 2;
+  while (m < n) m <<= 1;  // sort size: next power of two
+  for (int i = tid; i < m; i += VS_THREADS)
+    comp[i] = i < n ? (((unsigned long long)vox_key_of(pts[i], s) << 32) | (unsigned)i) : ~0ULL;
+  for (int k = 2; k <= m; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < m; i += VS_THREADS) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned long long a = comp[i], b = comp[p];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { comp[i] = b; comp[p] = a; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // head flags of the occupied voxels (finite points occupy the first n_valid sorted positions) + exclusive scan;
+  // thread t owns positions 2t and 2t+1
+  const int n_valid = s.n_valid;
+  uint32_t h0 = 0, h1 = 0;
+  {
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;
+    if (i0 < n_valid) h0 = (i0 == 0 || (uint32_t)(comp[i0] >> 32) != (uint32_t)(comp[i0 - 1] >> 32)) ? 1u : 0u;
+    if (i1 < n_valid) h1 = ((uint32_t)(comp[i1] >> 32) != (uint32_t)(comp[i1 - 1] >> 32)) ? 1u : 0u;
+  }
+  uint32_t x = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) swsum[w] = x;
+  __syncthreads();
+  uint32_t wb = 0, total_vox = 0;
+  for (int k = 0; k < VS_THREADS / 32; ++k) {
+    if (k < w) wb += swsum[k];
+    total_vox += swsum[k];
+  }
+  const uint32_t r0 = wb + x - (h0 + h1);
+  if (h0) seg[r0] = 2 * tid;
+  if (h1) seg[r0 + h0] = 2 * tid + 1;
+  if (tid == 0) seg[total_vox] = (uint32_t)n_valid;
+  __syncthreads();
+  for (uint32_t v = tid; v < total_vox; v += VS_THREADS) {
+    const uint32_t b = seg[v], e = seg[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (uint32_t t = b; t < e; ++t) {  // ascending input index: sequential f32 sums (A.1 step 7)
+      const float4 p = pts[(uint32_t)comp[t]];
+      sx += p.x; sy += p.y; sz += p.z; si += p.w;
+    }
+    const float c = (float)(e - b);
+    out[v] = make_float4(sx / c, sy / c, sz / c, si / c);
+  }
+  if (tid == 0) {
+    s.n_vox = total_vox;
+    *sp = s;
+  }
+}
+
 // f32 min/max + finite count of a cloud into mm[7] (ordered-uint encoding); shared with grid.cu
 cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm) {
   vox_minmax_init_kernel<<<1, 32, 0, c->stream>>>(mm);
@@ -278,6 +406,22 @@ int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& ou
   LIOGPU_CUDA_OK(c, out.reserve((size_t)n * sizeof(float4)));
   unsigned* mm = c->minmax.as<unsigned>();
   VoxelSetup* d_setup = c->vox_setup.as<VoxelSetup>();
+  VoxelSetup* h_setup = reinterpret_cast<VoxelSetup*>(c->h_pinned);
+  if (n <= VS_MAX) {  // small cloud: one block does everything
+    vox_small_kernel<<<1, VS_THREADS, 0, c->stream>>>(in, n, leaf, d_setup, out.as<float4>());
+    c->launches++;
+    LIOGPU_CUDA_OK(c, cudaGetLastError());
+    LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_setup, d_setup, sizeof(VoxelSetup), cudaMemcpyDeviceToHost, c->stream));
+    LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (h_setup->overflow) {  // q4
+      LIOGPU_CUDA_OK(c, cudaMemcpyAsync(out.p, in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+      *n_out = n;
+      *overflow = true;
+      return LIOGPU_OK;
+    }
+    *n_out = (int)h_setup->n_vox;
+    return LIOGPU_OK;
+  }
   LIOGPU_CUDA_OK(c, launch_minmax(c, in, n, mm));
   vox_setup_kernel<<<1, 32, 0, c->stream>>>(mm, leaf, d_setup);
   vox_key_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(in, n, d_setup, c->keys0.as<uint32_t>());
@@ -300,7 +444,6 @@ int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& ou
       in, sperm, c->seg_start.as<uint32_t>(), long_list, d_long, d_long + 1, out.as<float4>());
   c->launches += 3;
   LIOGPU_CUDA_OK(c, cudaGetLastError());
-  VoxelSetup* h_setup = reinterpret_cast<VoxelSetup*>(c->h_pinned);
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_setup, d_setup, sizeof(VoxelSetup), cudaMemcpyDeviceToHost, c->stream));
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   if (h_setup->overflow) {  // q4: PCL warns and returns the input unchanged

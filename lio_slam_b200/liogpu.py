@@ -60,7 +60,7 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -103,6 +103,8 @@ def load_library() -> C.CDLL:
     lib.liogpu_build_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                                            C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_merge_keyframes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                           C.c_int, C.POINTER(C.c_int)]
     lib.liogpu_default_local_map_params.argtypes = [C.POINTER(LocalMapParams)]
     lib.liogpu_default_local_map_params.restype = None
     lib.liogpu_publish_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -296,6 +298,22 @@ class LioGpu:
         self._check(st)
         d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "reserved"}
         return out[: n_out.value].copy(), d, st
+
+    def merge_keyframes(self, ids, poses, leaf: float = 0.0):
+        """saveMapService / publishGlobalMap / loopFindNearKeyframes cloud assembly -> (cloud (n,4), status)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        assert poses.shape[0] == ids.shape[0]
+        n_out = C.c_int(0)
+        out = np.empty((1, 4), np.float32)
+        st = self.lib.liogpu_merge_keyframes(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf),
+                                             out.ctypes.data, 16, out.shape[0], C.byref(n_out))
+        if st == E_CAPACITY:
+            out = np.empty((n_out.value, 4), np.float32)
+            st = self.lib.liogpu_merge_keyframes(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
+                                                 C.c_float(leaf), out.ctypes.data, 16, out.shape[0], C.byref(n_out))
+        self._check(st)
+        return out[: n_out.value].copy(), st
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

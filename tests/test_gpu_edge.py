@@ -349,3 +349,29 @@ def test_resident_cloud_is_invalidated_when_clobbered(oracle, small_case):
             g.scan2map(L.RESIDENT, small_case["guess"])
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 1023, 1024, 1025, 2047, 2048, 2049, 4100])
+def test_voxel_small_cloud_path_matches_pipeline(gpu, oracle, n):
+    """clouds of <= 2048 points (the key-pose filter, mapOptmization.cpp:1535-1536) take a single-block kernel;
+    sizes straddling the switch must all equal the oracle, including duplicates, non-finite points and the guard"""
+    rng = np.random.default_rng(n)
+    pts = np.c_[rng.uniform(-60, 60, (n, 2)), rng.uniform(-2, 6, (n, 1)), np.arange(n)].astype(np.float32)
+    pts[n // 3] = pts[0]                      # duplicate point
+    for leaf in (2.0, 0.3, 25.0):
+        want, ov = oracle.voxel_grid(pts, leaf)
+        got, st = gpu.voxel_downsample(pts, leaf)
+        assert st == (1 if ov else 0)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, leaf)
+    bad = pts.copy()
+    bad[::7, 1] = np.nan
+    bad[n // 2, 0] = np.inf
+    want, ov = oracle.voxel_grid(bad, 2.0)
+    got, st = gpu.voxel_downsample(bad, 2.0)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    want, ov = oracle.voxel_grid(pts, 1e-4)   # overflow guard -> input unchanged (for n >= 2 spread over 120 m)
+    got, st = gpu.voxel_downsample(pts, 1e-4)
+    assert st == (1 if ov else 0) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    allbad = np.full((min(n, 50), 4), np.nan, np.float32)
+    got, st = gpu.voxel_downsample(allbad, 2.0)
+    assert got.shape[0] == 0

@@ -194,3 +194,36 @@ def test_publish_local_map_realistic_size(gpu, world):
     clouds, poses = keyframes(world, nf, 50, beams=32, cols=900, step=0.5, seed0=700)
     got, info, _ = check(gpu, nf, clouds, poses, poses[-1], local_mapping_surf_leaf_size=0.2)
     assert info["n_concat"] > 300000
+
+
+def test_merge_keyframes_global_map_and_save_map(gpu, oracle, world, small_case):
+    """saveMapService (mapOptmization.cpp:936-950) / publishGlobalMap (:1031-1039) cloud assembly: transform +
+    concatenate (+ VoxelGrid), bit-exact, without touching the registration's local map"""
+    from lio_slam_b200.liogpu import LioGpuError
+    gpu.set_local_map(small_case["map4"])
+    p0, _, i0 = gpu.scan2map(small_case["scan4"], small_case["guess"])
+    clouds, poses = keyframes(world, oracle, 7, seed0=420)
+    ids = put(gpu, clouds)
+    raw = np.concatenate([oracle.transform_cloud(c, p) for c, p in zip(clouds, poses)])
+    got, st = gpu.merge_keyframes(ids, poses, 0.0)              # req.resolution == 0: the raw concatenation
+    assert st == 0
+    assert_biteq(got, raw, "globalSurfCloud")
+    for leaf in (0.4, 1.0):                                     # globalMapVisualizationLeafSize / req.resolution
+        want, ov = oracle.build_local_map(clouds, poses, leaf, threads=4)
+        got, st = gpu.merge_keyframes(ids, poses, leaf)
+        assert st == 0 and not ov
+        assert_biteq(got, want, f"leaf {leaf}")
+    sel = [5, 1, 3]                                             # the host's choice and order of key poses
+    want, _ = oracle.build_local_map([clouds[j] for j in sel], poses[sel], 0.4)
+    got, _ = gpu.merge_keyframes([ids[j] for j in sel], poses[sel], 0.4)
+    assert_biteq(got, want, "subset")
+    got, st = gpu.merge_keyframes(ids, poses, 0.001)            # overflow guard: input returned unchanged (q4)
+    assert st == 1
+    assert_biteq(got, raw, "guard")
+    got, st = gpu.merge_keyframes(np.zeros(0, np.int32), np.zeros((0, 6), np.float32), 0.4)
+    assert got.shape[0] == 0 and st == 0
+    with pytest.raises(LioGpuError):
+        gpu.merge_keyframes([4242], poses[:1], 0.4)
+    assert gpu.local_map_size() == small_case["map4"].shape[0]
+    p1, _, i1 = gpu.scan2map(small_case["scan4"], small_case["guess"])
+    assert np.array_equal(bits(p0), bits(p1)) and i0["iterations"] == i1["iterations"]
