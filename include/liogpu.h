@@ -197,6 +197,39 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
 int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k, float leaf,
                            void* xyzi_out, int out_stride, int cap_out, int* n_out);
 
+/* ---- loop-closure registration: pcl::IterativeClosestPoint<PointXYZI,PointXYZI> as configured
+ * at MO:1111-1121 (performRSLoopClosure) / MO:1203-1213 (performSCLoopClosure). */
+typedef struct liogpu_icp_params {
+  float  max_correspondence_distance; /* icp.setMaxCorrespondenceDistance(historyKeyframeSearchRadius*2)  MO:1112 */
+  int    max_iterations;              /* icp.setMaximumIterations(100)                                   MO:1113 */
+  double transformation_epsilon;      /* icp.setTransformationEpsilon(1e-6)                              MO:1114 */
+  double euclidean_fitness_epsilon;   /* icp.setEuclideanFitnessEpsilon(1e-6)                            MO:1115 */
+  float  cell_size;                   /* tuning only: cell edge of the target's neighbour grid, <= 0 = automatic */
+  int    reserved[5];
+} liogpu_icp_params;
+
+typedef struct liogpu_icp_info {
+  int    iterations;          /* nr_iterations_ */
+  int    converged;           /* icp.hasConverged() (MO:1123) */
+  int    convergence_state;   /* 1 iterations, 2 transform, 3 absolute MSE, 4 relative MSE, 5 no correspondences */
+  int    n_correspondences;   /* of the last iteration */
+  double fitness_score;       /* icp.getFitnessScore() (MO:1123, 1145) */
+  double last_mse;
+  float  gpu_ms;
+  int    reserved[5];
+} liogpu_icp_info;
+
+/* the settings of MO:1112-1116 for a given historyKeyframeSearchRadius (utility.h:321) */
+void liogpu_default_icp_params(liogpu_icp_params* p, float history_keyframe_search_radius);
+
+/* icp.setInputSource(cureKeyframeCloud); icp.setInputTarget(prevKeyframeCloud); icp.align(); (MO:1118-1121):
+ * point-to-point ICP with SVD alignment (Eigen::umeyama) and PCL's default convergence criteria.  The clouds are
+ * what liogpu_merge_keyframes returns for loopFindNearKeyframes (MO:1102-1103); the size guard of MO:1104 stays with
+ * the caller.  final_transformation = icp.getFinalTransformation(), row-major 4x4. */
+int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int source_stride,
+                     const void* target_xyzi, int n_target, int target_stride, const liogpu_icp_params* params,
+                     float final_transformation[16], liogpu_icp_info* info);
+
 /* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);

@@ -518,6 +518,37 @@ int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
 }
 
+void liogpu_default_icp_params(liogpu_icp_params* p, float history_keyframe_search_radius) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->max_correspondence_distance = history_keyframe_search_radius * 2;  // mapOptmization.cpp:1112
+  p->max_iterations = 100;                                              // :1113
+  p->transformation_epsilon = 1e-6;                                     // :1114
+  p->euclidean_fitness_epsilon = 1e-6;                                  // :1115
+}
+
+int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int source_stride, const void* target_xyzi,
+                     int n_target, int target_stride, const liogpu_icp_params* params, float final_transformation[16],
+                     liogpu_icp_info* info) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  liogpu_icp_info local_info;
+  if (!info) info = &local_info;
+  std::memset(info, 0, sizeof(*info));
+  if (!params || !final_transformation || n_source <= 0 || n_target <= 0 || params->max_iterations < 1 ||
+      !(params->max_correspondence_distance > 0.f) || source_xyzi == LIOGPU_DEVICE_RESIDENT ||
+      target_xyzi == LIOGPU_DEVICE_RESIDENT) {
+    c->err = "liogpu_icp_align: bad arguments";
+    return LIOGPU_E_INVALID;
+  }
+  rc = load_cloud(c, source_xyzi, n_source, source_stride, c->lm_b);
+  if (rc) return rc;
+  rc = load_cloud(c, target_xyzi, n_target, target_stride, c->lm_out);
+  if (rc) return rc;
+  return icp_align_dev(c, c->lm_b.as<float4>(), n_source, c->lm_out.as<float4>(), n_target, params, final_transformation, info);
+}
+
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
   int rc = enter(ctx);
   if (rc) return rc;

@@ -160,6 +160,9 @@ int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2,
 int publish_local_map_dev(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
                           float* d_T12, long long total, const float* h_yaw16, const liogpu_local_map_params* prm,
                           const float4** result, int* n_result, liogpu_local_map_info* info);
+// --- icp.cu
+int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, const liogpu_icp_params* prm,
+                  float final_T[16], liogpu_icp_info* info);
 // --- s2m.cu
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info);

@@ -19,6 +19,8 @@
 
 #include <math_constants.h>
 
+#include "shell_search.cuh"
+
 namespace liogpu {
 
 namespace {
@@ -79,7 +81,7 @@ struct TopK {
 #pragma unroll
     for (int j = 0; j < K; ++j) a[j] = CUDART_INF_F;
   }
-  __device__ __forceinline__ void push(float v) {
+  __device__ __forceinline__ void push(float v, float /*index bits*/ = 0.f) {
     if (v < a[K - 1]) {  // a value equal to the current worst leaves the multiset of the K smallest unchanged
 #pragma unroll
       for (int j = 0; j < K; ++j) {
@@ -97,75 +99,6 @@ struct TopK {
     return r;
   }
 };
-
-// FLANN L2_Simple<float> (same expression as the registration's search)
-__device__ __forceinline__ float sor_d2(const float4& a, const float4& b) {
-  float r = 0.f;
-  float d = a.x - b.x; r += d * d;
-  d = a.y - b.y;       r += d * d;
-  d = a.z - b.z;       r += d * d;
-  return r;
-}
-
-__device__ __forceinline__ int sor_cell(float p, float o, float inv_h, int n) {  // == grid.cu cell_coord
-  int c = (int)((p - o) * inv_h);
-  c = c < 0 ? 0 : c;
-  return c >= n ? n - 1 : c;
-}
-
-struct HomeCell {
-  int cx, cy, cz;
-  float fx, fy, fz;  // position of the point inside its cell: distance to the cell's lower faces
-};
-__device__ __forceinline__ HomeCell home_cell(const GridParams& g, const float4& p) {
-  HomeCell hc;
-  hc.cx = sor_cell(p.x, g.ox, g.inv_h, g.nx);
-  hc.cy = sor_cell(p.y, g.oy, g.inv_h, g.ny);
-  hc.cz = sor_cell(p.z, g.oz, g.inv_h, g.nz);
-  hc.fx = (p.x - g.ox) - (float)hc.cx * g.h;
-  hc.fy = (p.y - g.oy) - (float)hc.cy * g.h;
-  hc.fz = (p.z - g.oz) - (float)hc.cz * g.h;
-  return hc;
-}
-
-// After all cells within R rings of the home cell have been inspected, every point NOT inspected lies at least
-// `covered` away.  Returns the square of a safe lower bound of it (slack: f32 rounding of the cell assignment;
-// the relative margin covers the rounding of the squared distances), or +inf when the box is the whole grid.
-__device__ __forceinline__ float covered_d2(const GridParams& g, const HomeCell& hc, int R) {
-  const float Rh = (float)R * g.h;
-  float cov = CUDART_INF_F;
-  if (hc.cx - R > 0) cov = fminf(cov, Rh + hc.fx);
-  if (hc.cx + R < g.nx - 1) cov = fminf(cov, Rh + (g.h - hc.fx));
-  if (hc.cy - R > 0) cov = fminf(cov, Rh + hc.fy);
-  if (hc.cy + R < g.ny - 1) cov = fminf(cov, Rh + (g.h - hc.fy));
-  if (hc.cz - R > 0) cov = fminf(cov, Rh + hc.fz);
-  if (hc.cz + R < g.nz - 1) cov = fminf(cov, Rh + (g.h - hc.fz));
-  if (cov == CUDART_INF_F) return cov;
-  cov = fmaxf(cov - g.slack, 0.f) * 0.999999f;
-  return cov * cov;
-}
-
-template <int K>
-__device__ __forceinline__ void scan_range(const float4* __restrict__ sorted, unsigned b, unsigned e, const float4& p,
-                                           TopK<K>& top) {
-  for (unsigned t = b; t < e; ++t) top.push(sor_d2(p, __ldg(sorted + t)));
-}
-
-// the part of shell R (cells at Chebyshev distance exactly R from the home cell) that lies in row (y, z)
-template <int K>
-__device__ __forceinline__ void scan_shell_row(const float4* __restrict__ sorted, const uint32_t* __restrict__ cs,
-                                               const GridParams& g, const HomeCell& hc, int R, int y, int z,
-                                               const float4& p, TopK<K>& top) {
-  const unsigned row = ((unsigned)z * (unsigned)g.ny + (unsigned)y) * (unsigned)g.nx;
-  const int ady = y > hc.cy ? y - hc.cy : hc.cy - y, adz = z > hc.cz ? z - hc.cz : hc.cz - z;
-  if (ady == R || adz == R) {  // the whole x-run of the box is new: one contiguous range of the sorted array
-    const int x0 = max(hc.cx - R, 0), x1 = min(hc.cx + R, g.nx - 1);
-    scan_range<K>(sorted, __ldg(cs + row + x0), __ldg(cs + row + x1 + 1), p, top);
-  } else {                     // interior row: only the two end cells are new
-    if (hc.cx - R >= 0) scan_range<K>(sorted, __ldg(cs + row + hc.cx - R), __ldg(cs + row + hc.cx - R + 1), p, top);
-    if (hc.cx + R <= g.nx - 1) scan_range<K>(sorted, __ldg(cs + row + hc.cx + R), __ldg(cs + row + hc.cx + R + 1), p, top);
-  }
-}
 
 // dist_sum / mean_k exactly as PCL: sqrt in f32, accumulation in f64 in ascending order, neighbour 0 (the
 // query itself) skipped, narrowed to f32.
@@ -201,7 +134,7 @@ sor_knn_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ c
     const int z0 = max(hc.cz - R, 0), z1 = min(hc.cz + R, g.nz - 1);
     const int y0 = max(hc.cy - R, 0), y1 = min(hc.cy + R, g.ny - 1);
     for (int z = z0; z <= z1; ++z)
-      for (int y = y0; y <= y1; ++y) scan_shell_row<K>(sorted, cs, g, hc, R, y, z, p, top);
+      for (int y = y0; y <= y1; ++y) scan_shell_row(sorted, cs, g, hc, R, y, z, p, top);
     done = top.at(mean_k) <= covered_d2(g, hc, R);  // +inf bound: the whole grid has been inspected
   }
   if (done) md[__float_as_int(p.w)] = mean_distance<K>(top, mean_k);
@@ -259,7 +192,7 @@ sor_left_kernel(const float4* __restrict__ sorted, const uint32_t* __restrict__ 
       for (int r = lane; r < rows; r += 32) {
         const int z = hc.cz + r / side - R, y = hc.cy + r % side - R;
         if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
-        scan_shell_row<K>(sorted, cs, g, hc, R, y, z, p, top);
+        scan_shell_row(sorted, cs, g, hc, R, y, z, p, top);
       }
       const float kth = warp_extract<K>(top, mean_k + 1, lane, s, nullptr);
       done = kth <= covered_d2(g, hc, R);  // +inf bound: the whole grid has been inspected

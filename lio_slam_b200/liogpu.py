@@ -55,12 +55,24 @@ class LocalMapInfo(C.Structure):
                 ("sor_leftover", C.c_int), ("sor_exhaustive", C.c_int), ("reserved", C.c_int * 4)]
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_correspondence_distance", C.c_float), ("max_iterations", C.c_int),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
+                ("cell_size", C.c_float), ("reserved", C.c_int * 5)]
+
+
+class IcpInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("convergence_state", C.c_int),
+                ("n_correspondences", C.c_int), ("fitness_score", C.c_double), ("last_mse", C.c_double),
+                ("gpu_ms", C.c_float), ("reserved", C.c_int * 5)]
+
+
 EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liogpu_destroy", "liogpu_last_error",
            "liogpu_host_alloc", "liogpu_host_free", "liogpu_deskew", "liogpu_transform_cloud",
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -105,6 +117,10 @@ def load_library() -> C.CDLL:
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_merge_keyframes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                            C.c_int, C.POINTER(C.c_int)]
+    lib.liogpu_default_icp_params.argtypes = [C.POINTER(IcpParams), C.c_float]
+    lib.liogpu_default_icp_params.restype = None
+    lib.liogpu_icp_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.POINTER(IcpParams), C.c_void_p, C.POINTER(IcpInfo)]
     lib.liogpu_default_local_map_params.argtypes = [C.POINTER(LocalMapParams)]
     lib.liogpu_default_local_map_params.restype = None
     lib.liogpu_publish_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
@@ -314,6 +330,20 @@ class LioGpu:
                                                  C.c_float(leaf), out.ctypes.data, 16, out.shape[0], C.byref(n_out))
         self._check(st)
         return out[: n_out.value].copy(), st
+
+    def icp_align(self, source, target, history_keyframe_search_radius: float = 10.0, **over):
+        """pcl::IterativeClosestPoint as configured at mapOptmization.cpp:1111-1123 -> (T (4,4), info dict)."""
+        prm = IcpParams()
+        self.lib.liogpu_default_icp_params(C.byref(prm), C.c_float(history_keyframe_search_radius))
+        for k, v in over.items():
+            setattr(prm, k, v)
+        sp, sn, ss, keep_s = _cloud_args(source)
+        tp, tn, ts, keep_t = _cloud_args(target)
+        T = np.zeros(16, np.float32)
+        info = IcpInfo()
+        self._check(self.lib.liogpu_icp_align(self.h, sp, sn, ss, tp, tn, ts, C.byref(prm), T.ctypes.data, C.byref(info)))
+        d = {k: getattr(info, k) for k, _ in IcpInfo._fields_ if k != "reserved"}
+        return T.reshape(4, 4), d
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

@@ -224,6 +224,24 @@ int SYM(publish_local_map)(const float* clouds4, const int* offsets, const float
 }
 void SYM(yaw_frame_T)(const float* pose_now6, float* m12) { yaw_frame_T(pose_now6, m12); }
 
+// f3: pcl::IterativeClosestPoint::align + getFitnessScore as configured at MO:1111-1123.  brute != 0: exhaustive
+// nearest neighbour, else the KD-tree.
+int SYM(icp_align)(const float* source4, int ns, const float* target4, int nt, const IcpParams* prm, int brute,
+                   IcpResult* res, int threads) {
+  const P4* src = (const P4*)source4;
+  const P4* tgt = (const P4*)target4;
+  Index ix;
+  if (!brute) ix.build(tgt, nt);
+  auto nn = [&](const P4& q, int& idx, float& d2) {
+    Knn6 k;
+    if (brute) knn_brute(tgt, nt, q, k); else ix.knn(q, k);
+    idx = k.idx[0] == INT_MAX ? -1 : k.idx[0];
+    d2 = k.d2[0];
+  };
+  icp_align(src, ns, tgt, nn, *prm, *res, threads);
+  return res->converged;
+}
+
 // KD-tree handle (kdtreeSurfFromMap->setInputCloud, MO:1846).  The map memory must outlive the handle.
 void* SYM(index_build)(const float* map4, int nm) {
   Index* ix = new Index();

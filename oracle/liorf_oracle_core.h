@@ -771,4 +771,205 @@ inline int sor_mean_distances(int n, int mean_k, KnnFn knn, std::vector<float>& 
   return valid;
 }
 
+// ---------------------------------------------------------------------------------------------
+// f3: the loop-closure registration pcl::IterativeClosestPoint<PointXYZI,PointXYZI>::align as configured at
+// MO:1111-1121 (max correspondence distance 2*historyKeyframeSearchRadius, 100 iterations, transformation epsilon
+// 1e-6, Euclidean fitness epsilon 1e-6, no RANSAC) and icp.getFitnessScore() (MO:1123).  Restated [3P] from PCL
+// 1.10: registration/impl/icp.hpp (computeTransformation), correspondence_estimation.hpp
+// (determineCorrespondences: nearest neighbour, kept when dist^2 <= max_dist^2), transformation_estimation_svd.hpp
+// (Eigen::umeyama without scaling), default_convergence_criteria.hpp, registration.hpp (getFitnessScore).
+// Canonical arithmetic where Eigen's is not reproducible (vectorised f32 reductions, f32 JacobiSVD): sums of
+// coordinates and of products in f64 (products of two floats are exact), means and the 3x3 covariance rounded
+// to f32, rotation from a one-sided Jacobi SVD in f64 of that f32 matrix rounded to f32; everything else in the
+// operation order of the cited source.  Nearest-neighbour ties: lower target index.
+struct IcpParams {
+  double max_correspondence_distance;
+  int max_iterations;
+  double transformation_epsilon;
+  double euclidean_fitness_epsilon;
+};
+struct IcpResult {
+  float final_transformation[16];   // row-major 4x4
+  int iterations, converged, state, n_correspondences;
+  double fitness_score, last_mse;
+};
+enum { ICP_NOT_CONVERGED = 0, ICP_ITERATIONS = 1, ICP_TRANSFORM = 2, ICP_ABS_MSE = 3, ICP_REL_MSE = 4,
+       ICP_NO_CORRESPONDENCES = 5 };
+
+// R = U diag(1, 1, d) V^T of the f32 3x3 `sigma` (row-major), d = -1 on the smallest singular value when
+// det(U) det(V) < 0 (Eigen::umeyama Eq. 39-40).  One-sided Jacobi (Hestenes) in f64.
+inline void umeyama_rotation(const float sigma[9], float R[9]) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[i][j] = (double)sigma[3 * i + j];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; ++i) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
+        if (gamma == 0.0 || std::fabs(gamma) <= 1e-17 * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const double ap = A[i][p], aq = A[i][q];
+          A[i][p] = c * ap - sn * aq; A[i][q] = sn * ap + c * aq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - sn * vq; V[i][q] = sn * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double sv[3], U[3][3];
+  for (int j = 0; j < 3; ++j) sv[j] = std::sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+  int lo = 0;
+  if (sv[1] < sv[lo]) lo = 1;
+  if (sv[2] < sv[lo]) lo = 2;
+  const int a = (lo + 1) % 3, b = (lo + 2) % 3;
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) U[i][j] = sv[j] > 0.0 ? A[i][j] / sv[j] : 0.0;
+  if (!(sv[lo] > 1e-12 * (sv[a] > sv[b] ? sv[a] : sv[b]))) {  // rank-deficient: complete U right-handed
+    U[0][lo] = U[1][a] * U[2][b] - U[2][a] * U[1][b];
+    U[1][lo] = U[2][a] * U[0][b] - U[0][a] * U[2][b];
+    U[2][lo] = U[0][a] * U[1][b] - U[1][a] * U[0][b];
+  }
+  auto det3 = [](const double M[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+  };
+  const double d = det3(U) * det3(V) < 0.0 ? -1.0 : 1.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double r = U[i][a] * V[j][a] + U[i][b] * V[j][b] + d * (U[i][lo] * V[j][lo]);
+      R[3 * i + j] = (float)r;
+    }
+}
+
+// transformation_ (row-major 4x4 f32) from the f64 sums over the correspondences (Eigen::umeyama, no scaling)
+inline void umeyama_from_sums(const double S[16], int n, float T[16]) {
+  // S: sum src (3), sum tgt (3), sum tgt_i * src_j (9, row-major [i][j]), [15] unused
+  const double inv_n = 1.0 / (double)n;
+  float src_mean[3], dst_mean[3], sigma[9];
+  for (int a = 0; a < 3; ++a) { src_mean[a] = (float)(S[a] * inv_n); dst_mean[a] = (float)(S[3 + a] * inv_n); }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)   // one_over_n * dst_demean * src_demean^T
+      sigma[3 * i + j] = (float)((S[6 + 3 * i + j] - S[3 + i] * S[j] * inv_n) * inv_n);
+  float R[9];
+  umeyama_rotation(sigma, R);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) T[4 * i + j] = R[3 * i + j];
+    // Rt.col(m).head(m) = dst_mean; -= R * src_mean  (f32, products summed left to right)
+    T[4 * i + 3] = dst_mean[i] - (R[3 * i] * src_mean[0] + R[3 * i + 1] * src_mean[1] + R[3 * i + 2] * src_mean[2]);
+  }
+  T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+
+inline void mat4_mul(const float A[16], const float B[16], float C[16]) {  // Eigen Matrix4f product, f32
+  float t[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      t[4 * i + j] = A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j] + A[4 * i + 2] * B[8 + j] + A[4 * i + 3] * B[12 + j];
+  std::memcpy(C, t, sizeof(t));
+}
+
+// DefaultConvergenceCriteria::hasConverged; returns the convergence state
+struct IcpCriteria {
+  int max_iterations;
+  double rotation_threshold, translation_threshold, mse_threshold_relative, mse_threshold_absolute = 1e-12;
+  double prev_mse = DBL_MAX;
+  int check(int iterations, const float T[16], double cur_mse) {
+    if (iterations >= max_iterations) return ICP_ITERATIONS;
+    const float tr = T[0] + T[5] + T[10] - 1;
+    const double cos_angle = 0.5 * tr;
+    const float tsq = T[3] * T[3] + T[7] * T[7] + T[11] * T[11];
+    const double translation_sqr = tsq;
+    if (cos_angle >= rotation_threshold && translation_sqr <= translation_threshold) return ICP_TRANSFORM;
+    if (std::fabs(cur_mse - prev_mse) < mse_threshold_absolute) return ICP_ABS_MSE;
+    if (std::fabs(cur_mse - prev_mse) / prev_mse < mse_threshold_relative) return ICP_REL_MSE;
+    prev_mse = cur_mse;
+    return ICP_NOT_CONVERGED;
+  }
+};
+
+// nn(point, idx&, d2&): exact nearest neighbour in the target (ties: lower index).
+template <class NnFn>
+inline void icp_align(const P4* source, int ns, const P4* target, NnFn nn, const IcpParams& prm, IcpResult& res,
+                      int threads) {
+  std::vector<P4> cur(source, source + ns);
+  std::vector<int> idx(ns);
+  std::vector<float> d2(ns);
+  float finalT[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  IcpCriteria crit;
+  crit.max_iterations = prm.max_iterations;
+  crit.rotation_threshold = 1.0 - prm.transformation_epsilon;
+  crit.translation_threshold = prm.transformation_epsilon;
+  crit.mse_threshold_relative = prm.euclidean_fitness_epsilon;
+  const double max_d2 = prm.max_correspondence_distance * prm.max_correspondence_distance;
+  std::memset(&res, 0, sizeof(res));
+  int it = 0, state = ICP_NOT_CONVERGED;
+  do {
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int i = 0; i < ns; ++i) nn(cur[i], idx[i], d2[i]);
+    double S[16] = {0};
+    double mse = 0;
+    int cnt = 0;
+    for (int i = 0; i < ns; ++i) {
+      if (idx[i] < 0 || (double)d2[i] > max_d2) continue;
+      ++cnt;
+      mse += d2[i];
+    }
+    res.n_correspondences = cnt;
+    if (cnt < 3) { state = ICP_NO_CORRESPONDENCES; break; }   // min_number_correspondences_
+    mse /= (double)cnt;
+    res.last_mse = mse;
+    for (int i = 0; i < ns; ++i) {   // sums for umeyama (f64; every product of two floats is exact)
+      if (idx[i] < 0 || (double)d2[i] > max_d2) continue;
+      const P4& sp = cur[i];
+      const P4& tp = target[idx[i]];
+      const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
+      for (int a = 0; a < 3; ++a) {
+        S[a] += sv[a];
+        S[3 + a] += tv[a];
+        for (int b = 0; b < 3; ++b) S[6 + 3 * a + b] += tv[a] * sv[b];
+      }
+    }
+    float T[16];
+    umeyama_from_sums(S, cnt, T);
+    for (int i = 0; i < ns; ++i) {   // pcl::transformPointCloud(Matrix4f): x*c0 + (y*c1 + (z*c2 + c3))
+      const P4 p = cur[i];
+      cur[i].x = p.x * T[0] + (p.y * T[1] + (p.z * T[2] + T[3]));
+      cur[i].y = p.x * T[4] + (p.y * T[5] + (p.z * T[6] + T[7]));
+      cur[i].z = p.x * T[8] + (p.y * T[9] + (p.z * T[10] + T[11]));
+    }
+    mat4_mul(T, finalT, finalT);   // final_transformation_ = transformation_ * final_transformation_
+    ++it;
+    state = crit.check(it, T, mse);
+  } while (state == ICP_NOT_CONVERGED);
+  res.iterations = it;
+  res.state = state;
+  res.converged = (state != ICP_NOT_CONVERGED && state != ICP_NO_CORRESPONDENCES) ? 1 : 0;
+  std::memcpy(res.final_transformation, finalT, sizeof(finalT));
+  // getFitnessScore(): mean squared nearest-neighbour distance of the source moved by final_transformation_
+  double fit = 0;
+  int nr = 0;
+  std::vector<float> fd(ns);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (int i = 0; i < ns; ++i) {
+    const P4 p = source[i];
+    P4 q;
+    q.x = p.x * finalT[0] + (p.y * finalT[1] + (p.z * finalT[2] + finalT[3]));
+    q.y = p.x * finalT[4] + (p.y * finalT[5] + (p.z * finalT[6] + finalT[7]));
+    q.z = p.x * finalT[8] + (p.y * finalT[9] + (p.z * finalT[10] + finalT[11]));
+    q.i = p.i;
+    int j;
+    nn(q, j, fd[i]);
+    if (j < 0) fd[i] = -1.f;
+  }
+  for (int i = 0; i < ns; ++i)
+    if (fd[i] >= 0.f) { fit += fd[i]; ++nr; }
+  res.fitness_score = nr > 0 ? fit / nr : DBL_MAX;
+}
+
 }  // namespace liorf_oracle

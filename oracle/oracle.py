@@ -39,6 +39,17 @@ class LocalMapInfo(C.Structure):
                 ("sor_threshold", C.c_double)]
 
 
+class IcpParams(C.Structure):
+    _fields_ = [("max_correspondence_distance", C.c_double), ("max_iterations", C.c_int),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double)]
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("final_transformation", C.c_float * 16), ("iterations", C.c_int), ("converged", C.c_int),
+                ("state", C.c_int), ("n_correspondences", C.c_int), ("fitness_score", C.c_double),
+                ("last_mse", C.c_double)]
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
     if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")):
@@ -156,6 +167,20 @@ class Oracle:
                                      C.c_int(threads))
         d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "pad"}
         return out[: n_out.value].copy(), d, md[: info.n_cropped].copy()
+
+    # -- f3 -------------------------------------------------------------------------------------
+    def icp_align(self, source, target, max_correspondence_distance=20.0, max_iterations=100,
+                  transformation_epsilon=1e-6, euclidean_fitness_epsilon=1e-6, brute=False, threads: int = 1):
+        """pcl::IterativeClosestPoint as configured at MO:1111-1123 -> dict(T (4,4), iterations, converged, ...)."""
+        source, target = _f4(source), _f4(target)
+        prm = IcpParams(max_correspondence_distance, max_iterations, transformation_epsilon, euclidean_fitness_epsilon)
+        res = IcpResult()
+        self._f("icp_align")(_p(source, C.c_float), C.c_int(source.shape[0]), _p(target, C.c_float),
+                             C.c_int(target.shape[0]), C.byref(prm), C.c_int(1 if brute else 0), C.byref(res),
+                             C.c_int(threads))
+        return dict(T=np.array(res.final_transformation, np.float32).reshape(4, 4), iterations=res.iterations,
+                    converged=res.converged, state=res.state, n_correspondences=res.n_correspondences,
+                    fitness_score=res.fitness_score, last_mse=res.last_mse)
 
     # -- a5 / a7 --------------------------------------------------------------------------------
     def index_build(self, map4):
