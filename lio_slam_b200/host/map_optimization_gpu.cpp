@@ -189,6 +189,49 @@ void mapOptimization::saveKeyFrame() {  // :2128-2142 without the factor graph
   cloudKeyPoses6D.push_back(p6);
 }
 
+void mapOptimization::loopFindNearKeyframes(Cloud& nearKeyframes, int key, int searchNum) {  // :1360-1383
+  nearKeyframes.clear();
+  const int cloudSize = (int)cloudKeyPoses6D.size();
+  std::vector<int> ids;
+  std::vector<float> poses;
+  for (int i = -searchNum; i <= searchNum; ++i) {
+    const int keyNear = key + i;
+    if (keyNear < 0 || keyNear >= cloudSize) continue;
+    const PointTypePose& p = cloudKeyPoses6D[keyNear];
+    const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
+    ids.push_back(keyNear);
+    poses.insert(poses.end(), pose6, pose6 + 6);
+  }
+  if (ids.empty()) return;
+  int n = 0;
+  nearKeyframes.resize(1);
+  int st = liogpu_merge_keyframes(ctx_, ids.data(), poses.data(), (int)ids.size(), loopClosureICPSurfLeafSize,
+                                  nearKeyframes.data(), sizeof(PointType), 0, &n);   // downSizeFilterICP (:1378-1381)
+  if (st == LIOGPU_E_CAPACITY) {
+    nearKeyframes.resize(n);
+    st = liogpu_merge_keyframes(ctx_, ids.data(), poses.data(), (int)ids.size(), loopClosureICPSurfLeafSize,
+                                nearKeyframes.data(), sizeof(PointType), n, &n);
+  }
+  lastStatus = st;
+  nearKeyframes.resize(st < 0 ? 0 : n);
+}
+
+bool mapOptimization::loopClosureICP(int loopKeyCur, int loopKeyPre, float correctionLidarFrame[16], float* noiseScore) {
+  Cloud cureKeyframeCloud, prevKeyframeCloud;
+  loopFindNearKeyframes(cureKeyframeCloud, loopKeyCur, 0);                          // :1102
+  loopFindNearKeyframes(prevKeyframeCloud, loopKeyPre, historyKeyframeSearchNum);   // :1103
+  if (cureKeyframeCloud.size() < 300 || prevKeyframeCloud.size() < 1000) return false;  // :1104
+  liogpu_icp_params ip;
+  liogpu_default_icp_params(&ip, historyKeyframeSearchRadius);                     // :1112-1116
+  lastStatus = liogpu_icp_align(ctx_, cureKeyframeCloud.data(), (int)cureKeyframeCloud.size(), sizeof(PointType),
+                                prevKeyframeCloud.data(), (int)prevKeyframeCloud.size(), sizeof(PointType), &ip,
+                                correctionLidarFrame, &lastIcpInfo);
+  if (lastStatus < 0) return false;
+  if (!lastIcpInfo.converged || lastIcpInfo.fitness_score > historyKeyframeFitnessScore) return false;  // :1123
+  if (noiseScore) *noiseScore = (float)lastIcpInfo.fitness_score;                   // :1145
+  return true;
+}
+
 void mapOptimization::publishLocalMap() {  // :2442-2541; the reference calls it after every registration (:504)
   if (cloudKeyPoses3D.empty()) return;     // :2444
   const int thisPoseNum = (int)cloudKeyPoses3D.size();

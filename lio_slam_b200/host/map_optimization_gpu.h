@@ -83,6 +83,10 @@ class mapOptimization {
   liogpu_local_map_params localMapParams;
   liogpu_local_map_info lastLocalMapInfo{};
   Cloud localMapCloud;
+  // loop closure (utility.h:321-324, 305)
+  float historyKeyframeSearchRadius = 10.0f, historyKeyframeFitnessScore = 0.3f, loopClosureICPSurfLeafSize = 0.4f;
+  int historyKeyframeSearchNum = 25;
+  liogpu_icp_info lastIcpInfo{};
   liogpu_s2m_info lastInfo{};
   int lastStatus = 0;
 
@@ -96,6 +100,10 @@ class mapOptimization {
   Cloud transformPointCloud(const Cloud& in, const PointTypePose& pose);  // :849-868 -> liogpu_transform_cloud
   bool saveFrame() const;                                // :1909-1928 (host)
   void saveKeyFrame();                                   // the cloud/pose bookkeeping of saveKeyFramesAndFactor (:2128-2142)
+  void loopFindNearKeyframes(Cloud& nearKeyframes, int key, int searchNum);  // :1360-1383 -> liogpu_merge_keyframes
+  // the cloud / ICP part of performRSLoopClosure (:1098-1125): false when a guard rejects the closure;
+  // correctionLidarFrame = icp.getFinalTransformation() (row-major 4x4), noiseScore = icp.getFitnessScore()
+  bool loopClosureICP(int loopKeyCur, int loopKeyPre, float correctionLidarFrame[16], float* noiseScore);
   void publishLocalMap();                                // :2442-2541 -> liogpu_publish_local_map (fills localMapCloud)
   const char* lastError() const;
   liogpu_ctx* context() { return ctx_; }
