@@ -83,8 +83,8 @@ class mapOptimization {
   liogpu_local_map_params localMapParams;
   liogpu_local_map_info lastLocalMapInfo{};
   Cloud localMapCloud;
-  // loop closure (utility.h:321-324, 305)
-  float historyKeyframeSearchRadius = 10.0f, historyKeyframeFitnessScore = 0.3f, loopClosureICPSurfLeafSize = 0.4f;
+  // loop closure (utility.h:315, 321-324)
+  float historyKeyframeSearchRadius = 10.0f, historyKeyframeFitnessScore = 0.3f, loopClosureICPSurfLeafSize = 0.3f;
   int historyKeyframeSearchNum = 25;
   liogpu_icp_info lastIcpInfo{};
   liogpu_s2m_info lastInfo{};
