@@ -230,6 +230,16 @@ int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int
                      const void* target_xyzi, int n_target, int target_stride, const liogpu_icp_params* params,
                      float final_transformation[16], liogpu_icp_info* info);
 
+/* SCManager::makeScancontext (include/Scancontext.cpp:151-195) and the ring / sector keys (:198-225) that
+ * makeAndSaveScancontextAndKeys stores at every keyframe (MO:2151-2166).  desc is the 20 x 60 MatrixXd, row-major
+ * [ring][sector]; lidar_height = LIDAR_HEIGHT (Scancontext.h:80: 2.0), max_radius = PC_MAX_RADIUS (:84: 80.0).
+ * The cloud may be LIOGPU_DEVICE_RESIDENT (the deskewed sweep, SCInputType::SINGLE_SCAN_FULL). */
+#define LIOGPU_SC_NUM_RING 20
+#define LIOGPU_SC_NUM_SECTOR 60
+int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride, double lidar_height,
+                            double max_radius, double desc[LIOGPU_SC_NUM_RING * LIOGPU_SC_NUM_SECTOR],
+                            double ringkey[LIOGPU_SC_NUM_RING], double sectorkey[LIOGPU_SC_NUM_SECTOR]);
+
 /* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);

@@ -549,6 +549,32 @@ int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int
   return icp_align_dev(c, c->lm_b.as<float4>(), n_source, c->lm_out.as<float4>(), n_target, params, final_transformation, info);
 }
 
+int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride, double lidar_height, double max_radius,
+                            double* desc, double* ringkey, double* sectorkey) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!desc || !ringkey || !sectorkey || !(max_radius > 0.0)) { c->err = "liogpu_make_scancontext: bad arguments"; return LIOGPU_E_INVALID; }
+  const float4* pts = nullptr;
+  if (xyzi == LIOGPU_DEVICE_RESIDENT) {  // read in place, the resident cloud stays valid
+    if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
+    n = c->resident_n;
+    pts = c->resident->as<float4>();
+  } else {
+    rc = load_cloud(c, xyzi, n, stride, c->lm_b);
+    if (rc) return rc;
+    pts = c->lm_b.as<float4>();
+  }
+  double out[LIOGPU_SC_NUM_RING * LIOGPU_SC_NUM_SECTOR + LIOGPU_SC_NUM_RING + LIOGPU_SC_NUM_SECTOR];
+  rc = scancontext_dev(c, pts, n, lidar_height, max_radius, out);
+  if (rc) return rc;
+  const int bins = LIOGPU_SC_NUM_RING * LIOGPU_SC_NUM_SECTOR;
+  std::memcpy(desc, out, bins * sizeof(double));
+  std::memcpy(ringkey, out + bins, LIOGPU_SC_NUM_RING * sizeof(double));
+  std::memcpy(sectorkey, out + bins + LIOGPU_SC_NUM_RING, LIOGPU_SC_NUM_SECTOR * sizeof(double));
+  return LIOGPU_OK;
+}
+
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
   int rc = enter(ctx);
   if (rc) return rc;

@@ -160,6 +160,8 @@ int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2,
 int publish_local_map_dev(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
                           float* d_T12, long long total, const float* h_yaw16, const liogpu_local_map_params* prm,
                           const float4** result, int* n_result, liogpu_local_map_info* info);
+// --- scancontext.cu
+int scancontext_dev(Ctx* c, const float4* pts, int n, double lidar_height, double max_radius, double* h_out);
 // --- icp.cu
 int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, const liogpu_icp_params* prm,
                   float final_T[16], liogpu_icp_info* info);

@@ -72,7 +72,7 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -117,6 +117,8 @@ def load_library() -> C.CDLL:
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_merge_keyframes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                            C.c_int, C.POINTER(C.c_int)]
+    lib.liogpu_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
     lib.liogpu_default_icp_params.argtypes = [C.POINTER(IcpParams), C.c_float]
     lib.liogpu_default_icp_params.restype = None
     lib.liogpu_icp_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -344,6 +346,16 @@ class LioGpu:
         self._check(self.lib.liogpu_icp_align(self.h, sp, sn, ss, tp, tn, ts, C.byref(prm), T.ctypes.data, C.byref(info)))
         d = {k: getattr(info, k) for k, _ in IcpInfo._fields_ if k != "reserved"}
         return T.reshape(4, 4), d
+
+    def make_scancontext(self, cloud, lidar_height: float = 2.0, max_radius: float = 80.0):
+        """SCManager::makeScancontext + keys (Scancontext.cpp:151-225) -> (desc (20,60), ringkey, sectorkey), f64."""
+        ptr, n, stride, keep = _cloud_args(cloud)
+        desc = np.zeros((20, 60), np.float64)
+        rk = np.zeros(20, np.float64)
+        sk = np.zeros(60, np.float64)
+        self._check(self.lib.liogpu_make_scancontext(self.h, ptr, n, stride, lidar_height, max_radius, desc.ctypes.data,
+                                                     rk.ctypes.data, sk.ctypes.data))
+        return desc, rk, sk
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

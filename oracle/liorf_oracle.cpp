@@ -242,6 +242,12 @@ int SYM(icp_align)(const float* source4, int ns, const float* target4, int nt, c
   return res->converged;
 }
 
+// f3: SCManager::makeScancontext + ring / sector keys (Scancontext.cpp:151-225)
+void SYM(make_scancontext)(const float* scan4, int n, double lidar_height, double max_radius, double* desc,
+                           double* ringkey, double* sectorkey) {
+  make_scancontext((const P4*)scan4, n, lidar_height, max_radius, desc, ringkey, sectorkey);
+}
+
 // KD-tree handle (kdtreeSurfFromMap->setInputCloud, MO:1846).  The map memory must outlive the handle.
 void* SYM(index_build)(const float* map4, int nm) {
   Index* ix = new Index();

@@ -972,4 +972,54 @@ inline void icp_align(const P4* source, int ns, const P4* target, NnFn nn, const
   res.fitness_score = nr > 0 ? fit / nr : DBL_MAX;
 }
 
+// ---------------------------------------------------------------------------------------------
+// f3 (second half): the Scan Context descriptor of a keyframe cloud, SCManager::makeScancontext
+// (include/Scancontext.cpp:151-195) with xy2theta (:23-36), and its ring / sector keys (:198-225), computed at
+// every keyframe (MO:2156-2166).  No third-party arithmetic except libm: `sqrt` and `atan` are the C double
+// functions here (Scancontext.h has no `using namespace std`), the float arguments are widened, the results
+// narrowed where the source assigns to float.  desc is row-major [ring][sector] like the MatrixXd it replaces.
+// Non-finite points are skipped (the source would index with an undefined angle).  Key means: Eigen's
+// row.mean() = sum / size; the sums are exact in f64 for any realistic heights, so their order is immaterial.
+constexpr int SC_NUM_RING = 20, SC_NUM_SECTOR = 60;   // Scancontext.h:82-83
+
+inline float sc_xy2theta(const float& _x, const float& _y) {
+  if ((_x >= 0) & (_y >= 0)) return (float)((180 / M_PI) * std::atan((double)(_y / _x)));
+  if ((_x < 0) & (_y >= 0)) return (float)(180 - ((180 / M_PI) * std::atan((double)(_y / (-_x)))));
+  if ((_x < 0) & (_y < 0)) return (float)(180 + ((180 / M_PI) * std::atan((double)(_y / _x))));
+  return (float)(360 - ((180 / M_PI) * std::atan((double)((-_y) / _x))));
+}
+
+inline void make_scancontext(const P4* scan, int n, double lidar_height, double max_radius, double* desc,
+                             double* ringkey, double* sectorkey) {
+  const double NO_POINT = -1000;
+  for (int k = 0; k < SC_NUM_RING * SC_NUM_SECTOR; ++k) desc[k] = NO_POINT;
+  for (int i = 0; i < n; ++i) {
+    if (!std::isfinite(scan[i].x) || !std::isfinite(scan[i].y) || !std::isfinite(scan[i].z)) continue;
+    const float x = scan[i].x, y = scan[i].y;
+    const float z = (float)((double)scan[i].z + lidar_height);   // pt.z = z + LIDAR_HEIGHT (:167)
+    const float azim_range = (float)std::sqrt((double)(x * x + y * y));
+    const float azim_angle = sc_xy2theta(x, y);
+    if ((double)azim_range > max_radius) continue;
+    int ring_idx = (int)std::ceil(((double)azim_range / max_radius) * SC_NUM_RING);
+    ring_idx = std::max(std::min(SC_NUM_RING, ring_idx), 1);
+    const double sc = std::ceil(((double)azim_angle / 360.0) * SC_NUM_SECTOR);
+    int sctor_idx = std::isnan(sc) ? 0 : (int)sc;                 // x = y = 0: undefined in the source, bin 1 here
+    sctor_idx = std::max(std::min(SC_NUM_SECTOR, sctor_idx), 1);
+    double& d = desc[(ring_idx - 1) * SC_NUM_SECTOR + (sctor_idx - 1)];
+    if (d < (double)z) d = (double)z;
+  }
+  for (int k = 0; k < SC_NUM_RING * SC_NUM_SECTOR; ++k)
+    if (desc[k] == NO_POINT) desc[k] = 0;
+  for (int r = 0; r < SC_NUM_RING; ++r) {
+    double sum = 0;
+    for (int c = 0; c < SC_NUM_SECTOR; ++c) sum += desc[r * SC_NUM_SECTOR + c];
+    ringkey[r] = sum / SC_NUM_SECTOR;
+  }
+  for (int c = 0; c < SC_NUM_SECTOR; ++c) {
+    double sum = 0;
+    for (int r = 0; r < SC_NUM_RING; ++r) sum += desc[r * SC_NUM_SECTOR + c];
+    sectorkey[c] = sum / SC_NUM_RING;
+  }
+}
+
 }  // namespace liorf_oracle

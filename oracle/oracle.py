@@ -182,6 +182,16 @@ class Oracle:
                     converged=res.converged, state=res.state, n_correspondences=res.n_correspondences,
                     fitness_score=res.fitness_score, last_mse=res.last_mse)
 
+    def make_scancontext(self, scan4, lidar_height=2.0, max_radius=80.0):
+        """SCManager::makeScancontext + keys (Scancontext.cpp:151-225) -> (desc (20,60), ringkey (20,), sectorkey (60,))."""
+        scan4 = _f4(scan4)
+        desc = np.zeros((20, 60), np.float64)
+        rk = np.zeros(20, np.float64)
+        sk = np.zeros(60, np.float64)
+        self._f("make_scancontext")(_p(scan4, C.c_float), C.c_int(scan4.shape[0]), C.c_double(lidar_height),
+                                    C.c_double(max_radius), _p(desc, C.c_double), _p(rk, C.c_double), _p(sk, C.c_double))
+        return desc, rk, sk
+
     # -- a5 / a7 --------------------------------------------------------------------------------
     def index_build(self, map4):
         map4 = _f4(map4)
