@@ -384,7 +384,7 @@ icp_reduce_kernel(const IcpArgs A) {
 int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, const liogpu_icp_params* prm,
                   float final_T[16], liogpu_icp_info* info) {
   GridParams g;
-  const float cell = prm->cell_size > 0.f ? prm->cell_size : 1.0f;
+  const float cell = prm->cell_size > 0.f ? prm->cell_size : 0.5f;  // measured: 0.5 m 1.33 ms, 1 m 1.58 ms, 1.5 m 1.96 ms
   int rc = grid_build_core(c, tgt, nt, cell, 1.0f, 1.0f, c->sor_setup, c->sor_sorted, c->sor_cell_start, g);
   if (rc) return rc;
   const int rblocks = div_up(ns, RD_THREADS) < 256 ? div_up(ns, RD_THREADS) : 256;

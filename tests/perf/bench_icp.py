@@ -40,7 +40,15 @@ def main():
         T, info = g.icp_align(src, tgt)
         wall.append(1e3 * (time.perf_counter() - t0)); dev.append(info["gpu_ms"])
     assert info["iterations"] == want["iterations"] and np.abs(T - want["T"]).max() < 1e-4
-    print(json.dumps(dict(stage="loop-closure ICP (f3)", n_source=int(src.shape[0]), n_target=int(tgt.shape[0]),
+    cells = {}
+    for cell in (0.5, 0.75, 1.0, 1.5):
+        d = []
+        for _ in range(5):
+            Tc, ic = g.icp_align(src, tgt, cell_size=cell)
+            d.append(ic["gpu_ms"])
+        assert np.array_equal(Tc, T)
+        cells[str(cell)] = float(np.median(d[1:]))
+    print(json.dumps(dict(stage="loop-closure ICP (f3)", gpu_device_ms_by_cell_size=cells, n_source=int(src.shape[0]), n_target=int(tgt.shape[0]),
                           iterations=info["iterations"], converged=info["converged"], fitness=info["fitness_score"],
                           gpu_device_ms=float(np.median(dev[2:])), gpu_wall_ms=float(np.median(wall[2:])),
                           cpu_ms_all_threads=cpu_all, cpu_threads_all=os.cpu_count(), cpu_ms_1_thread=cpu_1,

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """The online per-sweep pipeline through the C ABI, sweep crossing PCIe once:
 liogpu_deskew (kept on device) -> liogpu_downsample_scan2map (resident) -> liogpu_keyframe_put (resident),
-for the 16-beam (configs[0]) and 32-beam + IMU (configs[1]) shapes, with the CPU oracle pipeline beside it.
+for the 16-beam (configs[0]) and 32-beam + IMU (configs[1]) shapes, with the CPU oracle pipeline beside it; then the
+two per-keyframe / per-scan extras of the fork: the Scan Context descriptor and publishLocalMap over 30 keyframes.
 Prints one JSON line per shape (wall ms per sweep, median of 30)."""
 import json
 import os
@@ -34,7 +35,17 @@ def main():
         guess = synth.perturbed_guess(pose_gt, 8)
         g.set_local_map(map4)
         dp = DeskewParams(beams, 1, 1, 1.0, 5.0, 2.0, 2.0, 1000.0, 100.0)
-        stage = {"deskew": [], "downsample+scan2map": [], "keyframe_put": [], "total": []}
+        # 30 earlier keyframes (utility.h:219 localMapKeyFramesNumber) for the per-scan publishLocalMap
+        kf_poses = []
+        for k in range(30):
+            pk = synth.path_pose(0.3 - 1.0 * (k + 1))
+            dsk_k, _ = o.voxel_grid(synth.to_packed(synth.make_scan(world, pk, beams, seed=200 + k, cols=900)), 0.4)
+            g.keyframe_put(k, dsk_k)
+            kf_poses.append(pk.astype(np.float32))
+        kf_ids = list(range(30))
+        kf_poses = np.array(kf_poses, np.float32)
+        stage = {"deskew": [], "downsample+scan2map": [], "keyframe_put": [], "total": [], "scancontext": [],
+                 "publishLocalMap": [], "total_with_scancontext_and_local_map": []}
         for s in range(35):
             a = time.perf_counter()
             n_dsk, _ = g.deskew(scan, t0, *imu, True, keep_on_device=True)
@@ -43,9 +54,16 @@ def main():
             c = time.perf_counter()
             g.keyframe_put(1000 + (s % 4), RESIDENT)
             d = time.perf_counter()
+            g.make_scancontext(RESIDENT)                      # SCInputType::SINGLE_SCAN_FEAT (mapOptmization.cpp:2158-2160)
+            e = time.perf_counter()
+            lm, lm_info, _ = g.publish_local_map(kf_ids, kf_poses, pose, use_removing_outliers=0,
+                                                 local_mapping_surf_leaf_size=0.2)      # jeep.yaml settings
+            f = time.perf_counter()
             if s >= 5:
                 stage["deskew"].append(b - a); stage["downsample+scan2map"].append(c - b)
                 stage["keyframe_put"].append(d - c); stage["total"].append(d - a)
+                stage["scancontext"].append(e - d); stage["publishLocalMap"].append(f - e)
+                stage["total_with_scancontext_and_local_map"].append(f - a)
         cpu = []
         h = None
         for s in range(4):
@@ -59,6 +77,7 @@ def main():
                           "iterations": info["iterations"],
                           "gpu_wall_ms": {k: round(1e3 * float(np.median(v)), 4) for k, v in stage.items()},
                           "cpu_ms": round(1e3 * float(np.median(cpu[1:])), 3), "cpu_threads": threads,
+                          "local_map_points": [lm_info["n_concat"], lm_info["n_out"]],
                           "h2d_bytes_per_sweep": int(scan.shape[0]) * 32, "pose_bit_equal": bool(np.array_equal(pose, ref_pose))}))
         g.close()
 
