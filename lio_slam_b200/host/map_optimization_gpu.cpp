@@ -48,7 +48,8 @@ void mapOptimization::extractNearby() {
   for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
     const PointType& p = cloudKeyPoses3D[i];
     const float d2 = (p.x - last.x) * (p.x - last.x) + (p.y - last.y) * (p.y - last.y) + (p.z - last.z) * (p.z - last.z);
-    if (d2 <= surroundingKeyframeSearchRadius * surroundingKeyframeSearchRadius) hits.emplace_back(d2, i);
+    // FLANN's radius result set keeps dist < radius^2 (strict), the squared radius narrowed to f32 by PCL
+    if (d2 < (float)((double)surroundingKeyframeSearchRadius * (double)surroundingKeyframeSearchRadius)) hits.emplace_back(d2, i);
   }
   std::sort(hits.begin(), hits.end());
   Cloud surroundingKeyPoses, ds(hits.size());
