@@ -240,6 +240,17 @@ int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride
                             double max_radius, double desc[LIOGPU_SC_NUM_RING * LIOGPU_SC_NUM_SECTOR],
                             double ringkey[LIOGPU_SC_NUM_RING], double sectorkey[LIOGPU_SC_NUM_SECTOR]);
 
+/* ---- key-pose selection: extractNearby (MO:1519-1554) + the guard of extractCloud (MO:1562).
+ * key_poses3d = cloudKeyPoses3D->points (x, y, z, intensity = keyframe index; n_key records of stride3d bytes),
+ * key_times = the `time` field of cloudKeyPoses6D->points (n_key doubles, time_stride bytes apart: 8 for a plain
+ * array, sizeof(PointTypePose) = 48 when pointing at cloudKeyPoses6D->points[0].time).  Radius search around the
+ * newest key pose, VoxelGrid(density_leaf) of the hits, each centroid snapped to its nearest key pose, the poses
+ * younger than 10 s appended, entries farther than search_radius dropped.  ids_out receives the keyframe indices in
+ * the order extractCloud concatenates them (duplicates kept); pass them to liogpu_build_local_map with their poses. */
+int liogpu_extract_nearby(liogpu_ctx* ctx, const void* key_poses3d, int n_key, int stride3d, const void* key_times,
+                          int time_stride, double time_laser_info_cur, float search_radius, float density_leaf,
+                          int* ids_out, int cap_ids, int* n_ids);
+
 /* kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (MO:1846) for a map built elsewhere:
  * install the cloud as the local map and build the grid index. */
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride);

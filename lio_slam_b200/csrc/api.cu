@@ -575,6 +575,27 @@ int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride
   return LIOGPU_OK;
 }
 
+int liogpu_extract_nearby(liogpu_ctx* ctx, const void* key_poses3d, int n_key, int stride3d, const void* key_times,
+                          int time_stride, double time_laser_info_cur, float search_radius, float density_leaf, int* ids_out,
+                          int cap_ids, int* n_ids) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!n_ids || n_key < 0 || (n_key > 0 && (!key_poses3d || !key_times)) || time_stride < 8 || cap_ids < 0 ||
+      (cap_ids > 0 && !ids_out) || !(search_radius > 0.f) || !(density_leaf > 0.f) || key_poses3d == LIOGPU_DEVICE_RESIDENT) {
+    c->err = "liogpu_extract_nearby: bad arguments";
+    return LIOGPU_E_INVALID;
+  }
+  *n_ids = 0;
+  if (n_key == 0) return LIOGPU_W_NO_KEYFRAMES;  // extractSurroundingKeyFrames returns at once (mapOptmization.cpp:1592)
+  rc = load_cloud(c, key_poses3d, n_key, stride3d, c->lm_a);
+  if (rc) return rc;
+  std::vector<double> times((size_t)n_key);
+  for (int i = 0; i < n_key; ++i) std::memcpy(&times[i], (const char*)key_times + (size_t)i * time_stride, sizeof(double));
+  return extract_nearby_dev(c, c->lm_a.as<float4>(), n_key, times.data(), time_laser_info_cur, search_radius, density_leaf,
+                            ids_out, cap_ids, n_ids);
+}
+
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
   int rc = enter(ctx);
   if (rc) return rc;

@@ -160,6 +160,9 @@ int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2,
 int publish_local_map_dev(Ctx* c, const float4* const* d_srcs, const int* d_offs, int k, const float* d_poses6,
                           float* d_T12, long long total, const float* h_yaw16, const liogpu_local_map_params* prm,
                           const float4** result, int* n_result, liogpu_local_map_info* info);
+// --- nearby.cu
+int extract_nearby_dev(Ctx* c, const float4* key3d, int n, const double* h_times, double time_cur, float radius,
+                       float density, int* ids, int cap, int* n_ids);
 // --- scancontext.cu
 int scancontext_dev(Ctx* c, const float4* pts, int n, double lidar_height, double max_radius, double* h_out);
 // --- icp.cu

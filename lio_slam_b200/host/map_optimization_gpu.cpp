@@ -43,6 +43,19 @@ void mapOptimization::extractSurroundingKeyFrames() {
 //   4. every keyframe younger than 10 s is appended WITHOUT de-duplication (:1545-1551) — a keyframe listed twice
 //      is concatenated twice by extractCloud, exactly as in the reference.
 void mapOptimization::extractNearby() {
+  if (selectKeyPosesOnDevice) {  // the same selection in one library call
+    std::vector<double> times(cloudKeyPoses6D.size());
+    for (size_t i = 0; i < times.size(); ++i) times[i] = cloudKeyPoses6D[i].time;
+    std::vector<int> ids(2 * cloudKeyPoses3D.size() + 1);
+    int n_ids = 0;
+    lastStatus = liogpu_extract_nearby(ctx_, cloudKeyPoses3D.data(), (int)cloudKeyPoses3D.size(), sizeof(PointType), times.data(),
+                                       sizeof(double), timeLaserInfoCur, surroundingKeyframeSearchRadius, surroundingKeyframeDensity,
+                                       ids.data(), (int)ids.size(), &n_ids);
+    ids.resize(lastStatus < 0 ? 0 : n_ids);
+    surroundingKeyPosesDS = ids;
+    extractCloudFromIds(ids);
+    return;
+  }
   const PointType& last = cloudKeyPoses3D.back();
   std::vector<std::pair<float, int>> hits;
   for (int i = 0; i < (int)cloudKeyPoses3D.size(); ++i) {
@@ -51,7 +64,7 @@ void mapOptimization::extractNearby() {
     // FLANN's radius result set keeps dist < radius^2 (strict), the squared radius narrowed to f32 by PCL
     if (d2 < (float)((double)surroundingKeyframeSearchRadius * (double)surroundingKeyframeSearchRadius)) hits.emplace_back(d2, i);
   }
-  std::sort(hits.begin(), hits.end());
+  std::sort(hits.begin(), hits.end());  // by distance, equal distances by index
   Cloud surroundingKeyPoses, ds(hits.size());
   for (const auto& h : hits) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
   int n_ds = 0;
@@ -67,22 +80,32 @@ void mapOptimization::extractNearby() {
       const float d2 = (p.x - ds[k].x) * (p.x - ds[k].x) + (p.y - ds[k].y) * (p.y - ds[k].y) + (p.z - ds[k].z) * (p.z - ds[k].z);
       if (d2 < bd) { bd = d2; best = i; }
     }
+    // extractCloud's guard (:1562) tests the CENTROID's position, not the pose it was snapped to
+    if (pointDistance(ds[k], last) > surroundingKeyframeSearchRadius) continue;
     ids.push_back((int)cloudKeyPoses3D[best].intensity);
   }
   for (int i = (int)cloudKeyPoses3D.size() - 1; i >= 0; --i) {
-    if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) ids.push_back(i);
-    else break;
+    if (timeLaserInfoCur - cloudKeyPoses6D[i].time < 10.0) {
+      if (pointDistance(cloudKeyPoses3D[i], last) > surroundingKeyframeSearchRadius) continue;
+      ids.push_back((int)cloudKeyPoses3D[i].intensity);
+    } else break;
   }
   surroundingKeyPosesDS = ids;
-  extractCloud(ids);
+  extractCloudFromIds(ids);
 }
 
 void mapOptimization::extractCloud(const std::vector<int>& ids) {
   std::vector<int> use;
-  std::vector<float> poses;
   for (int id : ids) {
     if (pointDistance(cloudKeyPoses3D[id], cloudKeyPoses3D.back()) > surroundingKeyframeSearchRadius) continue;  // :1562
     use.push_back(id);
+  }
+  extractCloudFromIds(use);
+}
+
+void mapOptimization::extractCloudFromIds(const std::vector<int>& use) {
+  std::vector<float> poses;
+  for (int id : use) {
     const PointTypePose& p = cloudKeyPoses6D[id];
     const float pose6[6] = {p.roll, p.pitch, p.yaw, p.x, p.y, p.z};
     poses.insert(poses.end(), pose6, pose6 + 6);

@@ -78,6 +78,7 @@ class mapOptimization {
   float surroundingKeyframeSearchRadius = 50.0f, surroundingKeyframeDensity = 2.0f;
   float surroundingkeyframeAddingDistThreshold = 1.0f, surroundingkeyframeAddingAngleThreshold = 0.2f;
   bool fetchLocalMap = false;      // copy laserCloudSurfFromMapDS back (it is only needed for publishing)
+  bool selectKeyPosesOnDevice = false;  // extractNearby through liogpu_extract_nearby (pays off on long runs)
   // publishLocalMap settings (utility.h:219-229) and its output cloud (tempCloud, :2541)
   int localMapKeyFramesNumber = 30;
   liogpu_local_map_params localMapParams;
@@ -94,6 +95,7 @@ class mapOptimization {
   void extractSurroundingKeyFrames();                    // :1590-1603
   void extractNearby();                                  // :1519-1554 (host: radius search + density filter + recency)
   void extractCloud(const std::vector<int>& ids);        // :1556-1588 -> liogpu_build_local_map
+  void extractCloudFromIds(const std::vector<int>& ids); // the part of extractCloud after the distance guard of :1562
   void downsampleCurrentScan();                          // :1605-1611 -> liogpu_voxel_downsample
   void scan2MapOptimization();                           // :1839-1865 -> liogpu_scan2map
   void downsampleAndScan2Map();                          // both fused on device -> liogpu_downsample_scan2map

@@ -18,7 +18,7 @@ using namespace liorf_gpu;
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s sequence.bin poses.txt [device] [scan_leaf] [map_leaf] [publish_local_map 0|1]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s sequence.bin poses.txt [device] [scan_leaf] [map_leaf] [publish_local_map 0|1] [select_key_poses_on_device 0|1]\n", argv[0]);
     return 2;
   }
   liogpu_params prm;
@@ -37,6 +37,7 @@ int main(int argc, char** argv) {
     double gpu_ms = 0, wall_ms = 0, lmap_ms = 0;
     int registered = 0, published = 0;
     const bool publish = argc > 6 && std::atoi(argv[6]) != 0;  // also run publishLocalMap after every scan (:504)
+    MO.selectKeyPosesOnDevice = argc > 7 && std::atoi(argv[7]) != 0;
     if (publish) {
       MO.localMapKeyFramesNumber = 50;                            // 6t.yaml:17
       MO.localMapParams.local_mapping_surf_leaf_size = 0.2f;      // jeep.yaml:23

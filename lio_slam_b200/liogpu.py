@@ -72,7 +72,7 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext", "liogpu_extract_nearby"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -119,6 +119,8 @@ def load_library() -> C.CDLL:
                                            C.c_int, C.POINTER(C.c_int)]
     lib.liogpu_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+    lib.liogpu_extract_nearby.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                          C.c_float, C.c_float, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     lib.liogpu_default_icp_params.argtypes = [C.POINTER(IcpParams), C.c_float]
     lib.liogpu_default_icp_params.restype = None
     lib.liogpu_icp_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -356,6 +358,18 @@ class LioGpu:
         self._check(self.lib.liogpu_make_scancontext(self.h, ptr, n, stride, lidar_height, max_radius, desc.ctypes.data,
                                                      rk.ctypes.data, sk.ctypes.data))
         return desc, rk, sk
+
+    def extract_nearby(self, key3d, key_time, time_cur: float, radius: float = 50.0, density: float = 2.0):
+        """extractNearby + extractCloud's guard (mapOptmization.cpp:1519-1565) -> keyframe indices, concatenation order."""
+        ptr, n, stride, keep = _cloud_args(key3d)
+        key_time = np.ascontiguousarray(key_time, np.float64)
+        assert key_time.shape[0] == n
+        ids = np.zeros(max(2 * n, 1), np.int32)
+        n_ids = C.c_int(0)
+        st = self._check(self.lib.liogpu_extract_nearby(self.h, ptr, n, stride, key_time.ctypes.data, 8, C.c_double(time_cur),
+                                                        C.c_float(radius), C.c_float(density), ids.ctypes.data, ids.shape[0],
+                                                        C.byref(n_ids)))
+        return ids[: n_ids.value].copy(), st
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

@@ -248,6 +248,16 @@ void SYM(make_scancontext)(const float* scan4, int n, double lidar_height, doubl
   make_scancontext((const P4*)scan4, n, lidar_height, max_radius, desc, ringkey, sectorkey);
 }
 
+// f4: extractNearby + the selection half of extractCloud (MO:1519-1565).  ids_out must hold 2*n entries.
+int SYM(extract_nearby)(const float* key3d4, const double* key_time, int n, double time_cur, float radius, float density,
+                        int* ids_out) {
+  std::vector<int> ids;
+  std::vector<P4> ds;
+  extract_nearby((const P4*)key3d4, key_time, n, time_cur, radius, density, ids, ds);
+  for (size_t k = 0; k < ids.size(); ++k) ids_out[k] = ids[k];
+  return (int)ids.size();
+}
+
 // KD-tree handle (kdtreeSurfFromMap->setInputCloud, MO:1846).  The map memory must outlive the handle.
 void* SYM(index_build)(const float* map4, int nm) {
   Index* ix = new Index();

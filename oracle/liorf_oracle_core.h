@@ -1022,4 +1022,50 @@ inline void make_scancontext(const P4* scan, int n, double lidar_height, double 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// f4: which keyframes form the local map — extractNearby (MO:1519-1554) and the selection half of extractCloud
+// (MO:1558-1565).  key3d = cloudKeyPoses3D (x, y, z, intensity = keyframe index), key_time = cloudKeyPoses6D[].time.
+// Third-party semantics restated [3P]: pcl::KdTreeFLANN::radiusSearch = every point with L2_Simple dist^2 strictly
+// below (float)(radius * radius) (FLANN RadiusResultSet), sorted by distance (ties: lower index here);
+// nearestKSearch(pt, 1) = the nearest key pose (ties: lower index); VoxelGrid as in voxel_grid().
+// ids receives, in the order extractCloud concatenates them, the keyframe index of every entry that survives the
+// distance guard of MO:1562 (duplicates are kept, as in the reference).
+inline float point_distance(const P4& p1, const P4& p2) {   // lib/common_lib.cpp:34-37
+  return (float)std::sqrt((double)((p1.x - p2.x) * (p1.x - p2.x) + (p1.y - p2.y) * (p1.y - p2.y) + (p1.z - p2.z) * (p1.z - p2.z)));
+}
+inline void extract_nearby(const P4* key3d, const double* key_time, int n, double time_laser_info_cur, float search_radius,
+                           float density_leaf, std::vector<int>& ids, std::vector<P4>& surrounding_ds) {
+  ids.clear();
+  surrounding_ds.clear();
+  if (n <= 0) return;
+  const P4& last = key3d[n - 1];
+  const float r2 = (float)((double)search_radius * (double)search_radius);
+  std::vector<std::pair<float, int>> hits;
+  for (int i = 0; i < n; ++i) {
+    const float d2 = l2_simple(last, key3d[i]);
+    if (d2 < r2) hits.emplace_back(d2, i);
+  }
+  std::stable_sort(hits.begin(), hits.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+  std::vector<P4> surrounding(hits.size());
+  for (size_t k = 0; k < hits.size(); ++k) surrounding[k] = key3d[hits[k].second];
+  voxel_grid(surrounding.data(), (int)surrounding.size(), density_leaf, surrounding_ds);   // MO:1535-1536
+  for (P4& pt : surrounding_ds) {                                                         // MO:1537-1541
+    int best = 0;
+    float bd = FLT_MAX;
+    for (int i = 0; i < n; ++i) {
+      const float d2 = l2_simple(pt, key3d[i]);
+      if (d2 < bd) { bd = d2; best = i; }
+    }
+    pt.i = key3d[best].i;
+  }
+  for (int i = n - 1; i >= 0; --i) {                                                      // MO:1544-1551
+    if (time_laser_info_cur - key_time[i] < 10.0) surrounding_ds.push_back(key3d[i]);
+    else break;
+  }
+  for (const P4& pt : surrounding_ds) {                                                   // MO:1560-1565
+    if (point_distance(pt, last) > search_radius) continue;
+    ids.push_back((int)pt.i);
+  }
+}
+
 }  // namespace liorf_oracle

@@ -192,6 +192,15 @@ class Oracle:
                                     C.c_double(max_radius), _p(desc, C.c_double), _p(rk, C.c_double), _p(sk, C.c_double))
         return desc, rk, sk
 
+    def extract_nearby(self, key3d, key_time, time_cur, radius=50.0, density=2.0):
+        """extractNearby + extractCloud's guard (MO:1519-1565) -> keyframe indices in concatenation order."""
+        key3d = _f4(key3d)
+        key_time = np.ascontiguousarray(key_time, dtype=np.float64)
+        ids = np.zeros(2 * max(key3d.shape[0], 1), np.int32)
+        n = self._f("extract_nearby")(_p(key3d, C.c_float), _p(key_time, C.c_double), C.c_int(key3d.shape[0]),
+                                      C.c_double(time_cur), C.c_float(radius), C.c_float(density), _p(ids, C.c_int))
+        return ids[:n].copy()
+
     # -- a5 / a7 --------------------------------------------------------------------------------
     def index_build(self, map4):
         map4 = _f4(map4)

@@ -116,6 +116,19 @@ def main():
                         gpu_wall_ms=wall_ms, cpu_ms=cpu1_ms, cpu_threads=1, cpu_ms_all_threads=cpuN_ms,
                         cpu_threads_all=os.cpu_count(), bit_equal=True,
                         algorithmic_bytes=16 * info["n_concat"] + 16 * info["n_out"]))
+    # ---- extractNearby: key-pose selection over a long run
+    rng = np.random.default_rng(12)
+    for n_key in (1000, 10000):
+        ang = np.cumsum(rng.normal(0, 0.05, n_key))
+        xyz = np.cumsum(np.c_[np.cos(ang), np.sin(ang), np.zeros(n_key)] * 0.8, axis=0)
+        key3d = np.c_[xyz, np.arange(n_key)].astype(np.float32)
+        kt = 0.4 * np.arange(n_key)
+        cpu_ms, want_ids = timeit(lambda: o.extract_nearby(key3d, kt, kt[-1] + 0.05), reps=3, warm=1)
+        wall_ms, (got_ids, _) = timeit(lambda: g.extract_nearby(key3d, kt, kt[-1] + 0.05))
+        assert np.array_equal(got_ids, want_ids)
+        res.append(dict(stage=f"extractNearby: radius search + density filter + snap + recency, {n_key} key poses", n_in=n_key,
+                        n_out=int(want_ids.shape[0]), gpu_device_ms=g.last_gpu_ms(), gpu_wall_ms=wall_ms, cpu_ms=cpu_ms,
+                        cpu_threads=1, bit_equal=True))
     # ---- index build alone (kdtreeSurfFromMap->setInputCloud), 500k-point map
     map4 = synth.make_local_map(world, 128, 500000, 0.2, seed=3, s0=-0.5)
     cpu_ms, h = timeit(lambda: o.index_build(map4), reps=3, warm=1)

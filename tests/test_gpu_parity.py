@@ -398,6 +398,11 @@ def test_replay_driver_tracks_ground_truth(world, tmp_path):
     assert r.returncode == 0, r.stderr
     s2 = json.loads(r.stdout.strip().splitlines()[-1])
     assert np.array_equal(np.loadtxt(out2), rows) and s2["local_map_points"] > 1000 and s2["local_map_gpu_ms_per_scan"] > 0
+    # and with the key poses selected on the device (liogpu_extract_nearby): the same keyframes, the same poses
+    out3 = str(tmp_path / "poses3.txt")
+    r = subprocess.run([exe, seq, out3, "0", "0.4", "0.5", "0", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.loadtxt(out3), rows)
 
 
 def test_device_resident_pipeline_config2(oracle, world):
