@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — scan-to-map registrations/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3|cfg3_leaf04|cfg1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one scan-to-map registration (liogpu_scan2map: the whole Gauss-Newton loop of
@@ -35,6 +35,8 @@ WORKLOADS = {
     # name: beams, n_map, map leaf, scan leaf (None = all points are queries), n_scans
     "cfg3": dict(beams=128, n_map=500_000, map_leaf=0.2, scan_leaf=None, cols=1800,
                  desc="128-beam sweep (230400 pts) vs 500k-pt local map, full LM loop on device"),
+    "cfg3_leaf04": dict(beams=128, n_map=500_000, map_leaf=0.2, scan_leaf=0.4, cols=1800,
+                        desc="128-beam sweep voxelised at the reference's default scan leaf 0.4 (~67k pts) vs 500k-pt local map"),
     "cfg1": dict(beams=16, n_map=40_000, map_leaf=0.5, scan_leaf=0.4, cols=1800,
                  desc="VLP-16 sweep (28800 pts, leaf 0.4) vs 40k-pt local map"),
 }
@@ -205,7 +207,8 @@ def main():
     # every rank runs the SAME synthetic sequence (its own copy, its own GPU, no communication): N-GPU work is
     # then exactly N x the 1-GPU work and the scaling number is not blurred by data-dependent iteration counts
     map4, scans, guesses = make_workload(name, 0, n_scans)
-    nq = int(scans[0].shape[0])
+    nqs = [int(sc.shape[0]) for sc in scans]       # voxelised sweeps differ in size from sweep to sweep
+    nq = int(round(sum(nqs) / len(nqs)))           # mean: byte counts below are per average step
     config["n_query"] = nq
     if os.environ.get("LIOGPU_BENCH_PRESORT"):  # experiment: spatially coherent query order
         from lio_slam_b200 import synth as _s
@@ -237,11 +240,11 @@ def main():
         torch.cuda.synchronize()
 
     def step_device(k):
-        pose, P, info = g.scan2map((dev_scans[k].data_ptr(), nq, 16), guesses[k], max_iter=MAX_ITER)
+        pose, P, info = g.scan2map((dev_scans[k].data_ptr(), nqs[k], 16), guesses[k], max_iter=MAX_ITER)
         return info
 
     def step_host(k):
-        pose, P, info = g.scan2map((host_recs[k].data_ptr(), nq, 32), guesses[k], max_iter=MAX_ITER)
+        pose, P, info = g.scan2map((host_recs[k].data_ptr(), nqs[k], 32), guesses[k], max_iter=MAX_ITER)
         return info
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -291,7 +294,7 @@ def main():
     for s in range(min(args.steps, 16) + 2):
         flush.fill_(s & 0xff)
         torch.cuda.synchronize()
-        _, _, inf = gp.scan2map((dev_scans[s % n_scans].data_ptr(), nq, 16), guesses[s % n_scans], max_iter=MAX_ITER)
+        _, _, inf = gp.scan2map((dev_scans[s % n_scans].data_ptr(), nqs[s % n_scans], 16), guesses[s % n_scans], max_iter=MAX_ITER)
         if s >= 2:
             kern["main_ms"] += inf["main_kernel_ms"]; kern["main_n"] += inf["main_kernel_launches"]
             kern["left_ms"] += inf["left_kernel_ms"]; kern["left_n"] += inf["left_kernel_launches"]
