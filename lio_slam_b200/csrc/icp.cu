@@ -14,6 +14,8 @@
 // has no correspondence).  getFitnessScore: the same search with no distance limit on the source moved by the final
 // transformation, f64 mean of the squared distances.
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "shell_search.cuh"
 
 namespace liogpu {
@@ -45,6 +47,8 @@ struct IcpArgs {
   uint32_t* left_list;      // [ns] shells 3.., then [ns] exhaustive
   double* partials;         // [reduce blocks][ICP_SUMS]
   int fitness;              // 1: getFitnessScore pass (source moved by finalT, no distance limit)
+  int all_warp;             // 1: every source point goes straight to the warp-per-point search (small sources: a
+                            //    thread-per-point pass would leave most of the GPU idle and is latency bound)
 };
 
 // nearest point: (bits(d^2) << 32 | target index), so that min() also breaks ties toward the lower index
@@ -134,16 +138,27 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 __global__ void __launch_bounds__(256)
 icp_left_kernel(const IcpArgs A) {
   __shared__ GridParams g;
+  __shared__ float sT[12];
   if (threadIdx.x == 0) g = *A.gp;
+  if (threadIdx.x < 12) sT[threadIdx.x] = A.fitness ? A.st->finalT[threadIdx.x] : A.st->T_inc[threadIdx.x];
   __syncthreads();
   if (!A.fitness && A.st->done) return;
   const double max_d2 = A.fitness ? CUDART_INF : A.st->max_d2;
+  const bool move = A.all_warp && (A.fitness || A.st->iter > 0);
   const int lane = threadIdx.x & 31;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const unsigned n_left = A.st->n_left;
+  const unsigned n_left = A.all_warp ? (unsigned)A.ns : A.st->n_left;
   for (unsigned w = warp; w < n_left; w += n_warps) {
-    const uint32_t i = A.left_list[w];
-    const float4 p = A.cur[i];
+    const uint32_t i = A.all_warp ? w : A.left_list[w];
+    float4 p = (A.all_warp && A.fitness) ? A.src[i] : A.cur[i];
+    if (move) {
+      p = se3(sT, p);
+      if (lane == 0) A.cur[i] = p;
+    }
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+      if (lane == 0) { A.nn_idx[i] = -1; A.nn_d2[i] = CUDART_INF_F; }
+      continue;
+    }
     const HomeCell hc = home_cell(g, p);
     Best1 best;
     best.init();
@@ -358,9 +373,18 @@ icp_reduce_kernel(const IcpArgs A) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < ICP_SUMS) {  // fixed order over the blocks
+  {  // fixed order: eight interleaved slices of the blocks (their loads in flight together), then the slices
+    const int q = threadIdx.x & 31, slice = threadIdx.x >> 5;
     double v = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) v += A.partials[(size_t)b * ICP_SUMS + threadIdx.x];
+    if (q < ICP_SUMS) {
+      for (unsigned b = slice; b < gridDim.x; b += RD_THREADS / 32) v += A.partials[(size_t)b * ICP_SUMS + q];
+      sh[slice][q] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ICP_SUMS) {
+    double v = 0.0;
+    for (int k = 0; k < RD_THREADS / 32; ++k) v += sh[k][threadIdx.x];
     sh[0][threadIdx.x] = v;
   }
   __syncthreads();
@@ -402,6 +426,7 @@ int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, 
   A.left_list = c->lm_left.as<uint32_t>();
   A.partials = reinterpret_cast<double*>((char*)c->lm_stats.p + 4096);
   A.fitness = 0;
+  A.all_warp = (ns <= 65536 && !getenv("LIOGPU_ICP_THREAD_PASS")) ? 1 : 0;
   IcpDevState* h = reinterpret_cast<IcpDevState*>((char*)c->h_pinned + 12288);
   memset(h, 0, sizeof(IcpDevState));
   for (int q = 0; q < 16; ++q) h->T_inc[q] = h->finalT[q] = (q % 5 == 0) ? 1.f : 0.f;
@@ -418,11 +443,11 @@ int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, 
   const int CHUNK = 10;
   int launched = 0;
   auto enqueue_iteration = [&](const IcpArgs& a) {
-    icp_nn_kernel<<<div_up(ns, NN_THREADS), NN_THREADS, 0, c->stream>>>(a);
-    icp_left_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(a);
+    if (!a.all_warp) icp_nn_kernel<<<div_up(ns, NN_THREADS), NN_THREADS, 0, c->stream>>>(a);
+    icp_left_kernel<<<a.all_warp ? c->sm_count * 8 : c->sm_count * 2, 256, 0, c->stream>>>(a);
     icp_brute_kernel<<<c->sm_count, BRT, 0, c->stream>>>(a);
     icp_reduce_kernel<<<rblocks, RD_THREADS, 0, c->stream>>>(a);
-    c->launches += 4;
+    c->launches += a.all_warp ? 3 : 4;
   };
   for (;;) {
     const int todo = (prm->max_iterations - launched) < CHUNK ? (prm->max_iterations - launched) : CHUNK;
