@@ -176,8 +176,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 10))
-        warm = max(1, min(args.warmup, 2))
+        # a step is one full CPU registration (~0.14 s on cfg3 with 16 threads): bounded so that the arm ends in
+        # well under a minute; at least 3 warm-up steps (the first parallel regions of a fresh process run slow)
+        steps = max(1, min(args.steps, 50))
+        warm = max(3, min(args.warmup, 10))
         map4, scans, guesses = make_workload(name, 0, 2)
         cb = cpu_baseline_run(name, map4, scans, guesses, steps, warm)
         config["n_query"] = int(scans[0].shape[0])
