@@ -42,6 +42,44 @@ def test_struct_layouts_match_header():
     assert C.sizeof(liogpu.S2MInfo) == 8 * 4 + 42 * 8 + 180 * 4 + 30 * 4 + 6 * 4
 
 
+def test_struct_layouts_match_a_c_compiler(tmp_path):
+    """sizeof / offsetof of every struct of include/liogpu.h as a C compiler lays them out == the ctypes mirrors"""
+    import os
+    import subprocess
+    from lio_slam_b200 import liogpu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("liogpu_params", liogpu.Params), ("liogpu_s2m_info", liogpu.S2MInfo),
+             ("liogpu_local_map_params", liogpu.LocalMapParams), ("liogpu_local_map_info", liogpu.LocalMapInfo),
+             ("liogpu_icp_params", liogpu.IcpParams), ("liogpu_icp_info", liogpu.IcpInfo)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "liogpu.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_local_map_and_icp_defaults_follow_the_reference():
+    from lio_slam_b200 import liogpu
+    lp = liogpu.local_map_params()
+    assert (lp.local_map_front, lp.local_map_left, lp.local_map_back, lp.local_map_right) == (70.0, 40.0, 20.0, 40.0)  # utility.h:220-223
+    assert lp.use_down_sampling == 1 and lp.use_removing_outliers == 1 and lp.mean_k == 10            # :224, 227, 228
+    assert abs(lp.local_mapping_surf_leaf_size - 0.01) < 1e-9 and lp.stddev_threshold == 1.0          # :226, 229
+    ip = liogpu.IcpParams()
+    liogpu.load_library().liogpu_default_icp_params(C.byref(ip), C.c_float(15.0))
+    assert ip.max_correspondence_distance == 30.0 and ip.max_iterations == 100                         # mapOptmization.cpp:1112-1113
+    assert ip.transformation_epsilon == 1e-6 and ip.euclidean_fitness_epsilon == 1e-6                  # :1114-1115
+
+
 def test_defaults_follow_utility_h():
     from lio_slam_b200 import liogpu
     p = liogpu.default_params()
