@@ -6,6 +6,8 @@
 2. path_small.npz : a small end-to-end case (scan, map, guess) with the oracle's outputs (VoxelGrid, one
    surfOptimization pass, the full scan2map loop).  These are ORACLE outputs, not reference outputs — the
    reference cannot be built here (parity unpinned); they guard the oracle and the CUDA path against drift.
+3. rows_f_small.npz : the same for the widened rows (publishLocalMap, keyframe merging, loop-closure ICP, Scan
+   Context, key-pose selection), again ORACLE outputs.
 """
 import os
 import sys
@@ -70,6 +72,47 @@ def make_path():
     print("path_small.npz: scan", scan4.shape, "ds", ds.shape, "map", map4.shape, "iters", info["iterations"])
 
 
+def make_rows_f():
+    """rows_f_small.npz: small cases of the widened rows with the oracle's outputs."""
+    from lio_slam_b200 import synth
+    from oracle.oracle import Oracle
+    o = Oracle("port")
+    world = synth.make_world(1234)
+    clouds, poses = [], []
+    for k in range(4):
+        p = synth.path_pose(1.0 * k)
+        ds, _ = o.voxel_grid(synth.to_packed(synth.make_scan(world, p, 16, seed=40 + k, cols=200)), 0.4)
+        clouds.append(ds)
+        poses.append(p.astype(np.float32))
+    poses = np.array(poses, np.float32)
+    offs = np.zeros(5, np.int32)
+    offs[1:] = np.cumsum([c.shape[0] for c in clouds])
+    now = np.array([0.01, -0.02, 2.0, 7.5, 1.0, 1.8], np.float32)
+    lm, lm_info, md = o.publish_local_map(clouds, poses, now, leaf=0.3, threads=4)
+    merged, _ = o.build_local_map(clouds, poses, 0.4, threads=4)
+    wrong = poses[2].copy()
+    wrong[3] += 0.5
+    wrong[4] -= 0.3
+    wrong[2] += 0.02
+    src = o.transform_cloud(clouds[2], wrong)
+    icp = o.icp_align(src, merged, threads=4)
+    sc, rk, sk = o.make_scancontext(clouds[0])
+    n = 120
+    xyz = np.array([synth.path_pose(0.7 * k)[3:6] for k in range(n)])
+    key3d = np.c_[xyz, np.arange(n)].astype(np.float32)
+    key_t = 0.5 * np.arange(n)
+    ids = o.extract_nearby(key3d, key_t, key_t[-1] + 0.1, 30.0, 2.0)
+    np.savez_compressed(os.path.join(HERE, "rows_f_small.npz"), clouds=np.concatenate(clouds), offsets=offs, poses=poses,
+                        pose_now=now, local_map=lm, local_map_counts=np.array([lm_info["n_concat"], lm_info["n_cropped"],
+                                                                               lm_info["n_after_sor"], lm_info["n_out"]]),
+                        mean_distances=md, merged=merged, icp_source=src, icp_T=icp["T"],
+                        icp_ints=np.array([icp["iterations"], icp["converged"], icp["state"], icp["n_correspondences"]]),
+                        icp_fitness=np.array(icp["fitness_score"]), sc_desc=sc, sc_ringkey=rk, sc_sectorkey=sk,
+                        key3d=key3d, key_time=key_t, nearby_ids=ids)
+    print("rows_f_small.npz: local map", lm.shape, "icp iters", icp["iterations"], "nearby ids", ids.shape)
+
+
 if __name__ == "__main__":
     make_cv2()
     make_path()
+    make_rows_f()

@@ -369,6 +369,30 @@ def test_scan2map_full_size_properties(gpu):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2]["JtJ"], b[2]["JtJ"])
 
 
+def test_gpu_matches_committed_golden_rows_f(gpu):
+    """the widened rows against the committed fixture (tests/golden/rows_f_small.npz) — no oracle involved at run time"""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "rows_f_small.npz"))
+    offs = G["offsets"]
+    clouds = [np.ascontiguousarray(G["clouds"][offs[k]:offs[k + 1]]) for k in range(len(offs) - 1)]
+    gpu.keyframe_clear()
+    for k, c in enumerate(clouds):
+        gpu.keyframe_put(k, c)
+    ids = list(range(len(clouds)))
+    lm, info, st = gpu.publish_local_map(ids, G["poses"], G["pose_now"], local_mapping_surf_leaf_size=0.3)
+    assert_biteq(lm, G["local_map"], "golden publishLocalMap")
+    assert [info["n_concat"], info["n_cropped"], info["n_after_sor"], info["n_out"]] == G["local_map_counts"].tolist()
+    merged, _ = gpu.merge_keyframes(ids, G["poses"], 0.4)
+    assert_biteq(merged, G["merged"], "golden merged keyframes")
+    T, ii = gpu.icp_align(G["icp_source"], merged)
+    assert [ii["iterations"], ii["converged"], ii["convergence_state"], ii["n_correspondences"]] == G["icp_ints"].tolist()
+    assert np.abs(T - G["icp_T"]).max() <= 1e-5 and ii["fitness_score"] == pytest.approx(float(G["icp_fitness"]), rel=1e-6)
+    sc, rk, sk = gpu.make_scancontext(clouds[0])
+    assert np.array_equal(sc, G["sc_desc"]) and np.array_equal(rk, G["sc_ringkey"]) and np.array_equal(sk, G["sc_sectorkey"])
+    got, _ = gpu.extract_nearby(G["key3d"], G["key_time"], float(G["key_time"][-1]) + 0.1, 30.0, 2.0)
+    assert np.array_equal(got, G["nearby_ids"])
+
+
 def test_replay_driver_tracks_ground_truth(world, tmp_path):
     # the C++ host mirror (lio_slam_b200/host) driving the C ABI over a short sequence: keyframes are
     # added by the reference's saveFrame rule, the local map is rebuilt from device-resident keyframes,

@@ -165,3 +165,25 @@ def test_knn_against_scipy_ckdtree(oracle):
     assert ok.mean() > 0.95
     assert np.array_equal(idx[ok], ii[ok, :5])
     assert np.abs(np.sqrt(d2[ok].astype(np.float64)) - dd[ok, :5]).max() < 1e-5
+
+
+def test_golden_rows_f_small(oracle):
+    """the committed small cases of the widened rows (publishLocalMap, merging, ICP, Scan Context, key-pose selection):
+    the oracle still produces exactly what tests/golden/make_golden.py stored"""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "rows_f_small.npz"))
+    offs = G["offsets"]
+    clouds = [G["clouds"][offs[k]:offs[k + 1]] for k in range(len(offs) - 1)]
+    lm, info, md = oracle.publish_local_map(clouds, G["poses"], G["pose_now"], leaf=0.3, threads=2)
+    assert np.array_equal(lm.view(np.uint32), G["local_map"].view(np.uint32))
+    assert [info["n_concat"], info["n_cropped"], info["n_after_sor"], info["n_out"]] == G["local_map_counts"].tolist()
+    assert np.array_equal(md.view(np.uint32), G["mean_distances"].view(np.uint32))
+    merged, _ = oracle.build_local_map(clouds, G["poses"], 0.4, threads=2)
+    assert np.array_equal(merged.view(np.uint32), G["merged"].view(np.uint32))
+    icp = oracle.icp_align(G["icp_source"], merged, threads=2)
+    assert np.array_equal(icp["T"].view(np.uint32), G["icp_T"].view(np.uint32))
+    assert [icp["iterations"], icp["converged"], icp["state"], icp["n_correspondences"]] == G["icp_ints"].tolist()
+    assert icp["fitness_score"] == float(G["icp_fitness"])
+    sc, rk, sk = oracle.make_scancontext(clouds[0])
+    assert np.array_equal(sc, G["sc_desc"]) and np.array_equal(rk, G["sc_ringkey"]) and np.array_equal(sk, G["sc_sectorkey"])
+    ids = oracle.extract_nearby(G["key3d"], G["key_time"], G["key_time"][-1] + 0.1, 30.0, 2.0)
+    assert np.array_equal(ids, G["nearby_ids"])
