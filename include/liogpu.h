@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LIOGPU_ABI_VERSION 1
+#define LIOGPU_ABI_VERSION 2
 
 /* status codes */
 #define LIOGPU_OK 0
@@ -71,8 +71,13 @@ typedef struct liogpu_params {
   float knn_cell_size;       /* edge of the sorted-grid cell used for the 5-NN index; 0 = auto   */
   float knn_phase1_radius;   /* radius of the cheap first search phase; 0 = auto (2 x map leaf),
                                 < 0 = single phase.  Tuning only: results do not depend on it.   */
-  int profile_kernels;       /* 1: time every kernel of the LM loop with CUDA events (bench.py)  */
-  int reserved[5];
+  int profile_kernels;       /* 1: time the phases of the LM loop on the device (bench.py)        */
+  int s2m_path;              /* 0 = the whole LM loop as ONE persistent cooperative launch (default);
+                                1 = two launches per iteration (the round-1 path, kept for A/B runs).
+                                Tuning only: results do not depend on it.                          */
+  int s2m_no_certificate;    /* 1 = never use the exact no-search certificate (A/B runs): every point
+                                with a candidate set is searched again.  Results do not depend on it. */
+  int reserved[3];
 } liogpu_params;
 
 /* Result block of liogpu_scan2map (everything the reference keeps in members after the loop). */
@@ -94,9 +99,17 @@ typedef struct liogpu_s2m_info {
   float gpu_ms;      /* device time of the loop (CUDA events on the context's stream)              */
   int seeded;        /* last iteration: points whose search started from the previous neighbours   */
   /* filled only when params.profile_kernels != 0 (CUDA events around every launch of the first chunk): */
-  float main_kernel_ms;   /* summed device time of s2m_main_kernel over the executed iterations    */
-  float left_kernel_ms;   /* summed device time of s2m_left_kernel over the executed iterations    */
-  int main_kernel_launches, left_kernel_launches; /* executed (not early-exit) launches timed      */
+  float main_kernel_ms;   /* summed device time of the search + plane-fit phase over the executed iterations
+                             (s2m_path 1: of s2m_main_kernel)                                       */
+  float left_kernel_ms;   /* summed device time of the leftover search + reduction + 6x6 tail
+                             (s2m_path 1: of s2m_left_kernel)                                       */
+  int main_kernel_launches, left_kernel_launches; /* executed iterations timed                     */
+  /* s2m_path 0 only: */
+  int certified;     /* last iteration: points whose 5 neighbours came from the exact certificate  */
+  int leftovers;     /* last iteration: points finished by the warp-cooperative full-gate search   */
+  float tail_ms;     /* profile_kernels: summed time between a CTA's partial row and the release of
+                        the next iteration (fixed-order reduction + 6x6 tail + barrier)            */
+  int kernel_launches; /* kernels launched by this call                                            */
 } liogpu_s2m_info;
 
 int liogpu_abi_version(void);
@@ -284,6 +297,14 @@ int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int str
 int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int stride,
                              const float* pose6, const float* T12, int* nn_idx, float* nn_d2,
                              float* coeff, unsigned char* flag, unsigned char* tie);
+
+/* liogpu_scan2map with the per-point results of its LAST EXECUTED iteration exposed (same outputs and meaning as
+ * liogpu_surf_optimization; any pointer may be NULL).  Parity tests use it to check every iteration of the
+ * on-device loop — including the ones that take the no-search certificate — against a surfOptimization pass of the
+ * reference at the pose that iteration started from (info->pose_hist).  Runs the one-launch loop (s2m_path 0). */
+int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6],
+                          float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info,
+                          int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag, unsigned char* tie);
 
 /* Timing hook for bench.py: device milliseconds of the last call's kernels (events on ctx's stream). */
 float liogpu_last_gpu_ms(const liogpu_ctx* ctx);

@@ -208,7 +208,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan,
+                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.fz_rows, &c.fz_left, &c.fz_lb, &c.fz_probe, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan,
                     &c.lm_flag, &c.lm_pos, &c.lm_a, &c.lm_b, &c.lm_md, &c.lm_left, &c.lm_out, &c.lm_stats, &c.sor_setup,
                     &c.sor_sorted, &c.sor_cell_start};
   for (DevBuf* b : bufs) b->release();
@@ -646,6 +646,29 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
   if (rc) return rc;
   if (scan_ds != LIOGPU_DEVICE_RESIDENT) clobber(c, &c->scan_ds4);
   return scan2map_dev(c, c->scan_ds4.as<float4>(), n, pose_io, matP_io, degenerate_io, max_iter, info);
+}
+
+int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6], float matP_io[36],
+                          int* degenerate_io, int max_iter, liogpu_s2m_info* info, int* nn_idx, float* nn_d2, float* coeff,
+                          unsigned char* flag, unsigned char* tie) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  if (!pose_io || !matP_io || !degenerate_io) { c->err = "liogpu_scan2map_trace: null state pointer"; return LIOGPU_E_INVALID; }
+  if (scan_ds == LIOGPU_DEVICE_RESIDENT) {
+    if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
+    n = c->resident_n;
+  }
+  rc = s2m_guards(c, n, info);
+  if (rc) {
+    if (info) info->is_degenerate = *degenerate_io;
+    return rc;
+  }
+  rc = load_cloud(c, scan_ds, n, stride, c->scan_ds4);
+  if (rc) return rc;
+  if (scan_ds != LIOGPU_DEVICE_RESIDENT) clobber(c, &c->scan_ds4);
+  return scan2map_trace_dev(c, c->scan_ds4.as<float4>(), n, pose_io, matP_io, degenerate_io, max_iter, info, nn_idx, nn_d2,
+                            coeff, flag, tie);
 }
 
 int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int stride, float pose_io[6],

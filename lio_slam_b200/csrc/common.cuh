@@ -61,6 +61,8 @@ struct GridParams {
   float gate1_d2;     // squared radius of the cheap first search phase (>= gate_d2 disables it)
 };
 
+#define LIOGPU_FZ_K 8  // members of a point's candidate set (s2m_fused.cuh)
+
 // ---- state of the LM loop kept on device between iterations (MO:171,176,177) ----
 struct LmDevState {
   float T[12];     // transPointAssociateToMap of `pose` (MO:1615), refreshed after every pose update
@@ -84,6 +86,15 @@ struct LmDevState {
   int eig_pending;    // 1: matP still has to be computed from AtA0 by lm_matp_kernel
   int cert_mismatch;  // must stay 0: the side computation contradicted the non-degeneracy certificate
   int seeded;         // points of the last executed iteration that started from the previous neighbours
+  // ---- fused persistent loop (s2m_fused.cuh); zeroed with the rest of the block at every registration ----
+  float T_prev[12];   // transform of the previous iteration: where every point stood when its candidate set was certified
+  unsigned fz_barrier;                 // grid barrier counter (monotonic)
+  unsigned fz_ticket;                  // end-of-iteration ticket (monotonic)
+  unsigned fz_release;                 // iterations whose 6x6 tail has finished
+  unsigned fz_queue[LIOGPU_MAX_ITER];  // chunk queue head, one per iteration
+  int certified;      // last executed iteration: points whose five neighbours came from the certificate (no grid walk)
+  int leftovers;      // last executed iteration: points finished by the warp-cooperative full-gate search
+  int pad_[1];
 };
 
 // host-visible context
@@ -113,6 +124,9 @@ struct Ctx {
   DevBuf keys0, keys1, vals0, vals1, counters, scan_tmp, seg_flag, seg_start;
   // small device structs
   DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf, prev_nn, hopeless;
+  // fused persistent loop: per-chunk / per-CTA partial rows, leftover segments, candidate-set bounds, probes
+  DevBuf fz_rows, fz_left, fz_lb, fz_probe;
+  int fz_grid = 0;        // CTAs of the cooperative launch (0 = not yet queried, < 0 = unavailable)
   // per-point debug outputs of surf_optimization
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
   // pinned host mirrors
@@ -171,6 +185,9 @@ int icp_align_dev(Ctx* c, const float4* src, int ns, const float4* tgt, int nt, 
 // --- s2m.cu
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info);
+int scan2map_trace_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                       int max_iter, liogpu_s2m_info* info, int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag,
+                       unsigned char* tie);
 int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6, const float* T12, int* nn_idx,
                           float* nn_d2, float* coeff, unsigned char* flag, unsigned char* tie);
 // --- deskew.cu

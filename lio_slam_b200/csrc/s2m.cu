@@ -1160,6 +1160,10 @@ s2m_left_kernel(const S2mArgs A) {
   }
 }
 
+}  // namespace liogpu
+#include "s2m_fused.cuh"
+namespace liogpu {
+
 // Both kernels of an iteration are launched with programmatic stream serialization: the next grid is scheduled
 // as the previous one drains (its last block is still reducing / solving the 6x6 system) and waits in
 // cudaGridDependencySynchronize(), which hides the launch latency between dependent kernels.
@@ -1219,11 +1223,158 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   return LIOGPU_OK;
 }
 
+static void fill_info(Ctx* c, const LmDevState* h, int n, liogpu_s2m_info* info) {
+  info->iterations = h->iter;
+  info->converged = h->converged;
+  info->n_query = n;
+  info->n_sel = h->n_sel;
+  info->is_degenerate = h->degenerate;
+  info->tie_queries = h->tie_queries;
+  info->delta_r_deg = h->delta_r;
+  info->delta_t_cm = h->delta_t;
+  memcpy(info->JtJ, h->JtJ, sizeof(info->JtJ));
+  memcpy(info->Jtr, h->Jtr, sizeof(info->Jtr));
+  memcpy(info->pose_hist, h->pose_hist, sizeof(info->pose_hist));
+  memcpy(info->nsel_hist, h->nsel_hist, sizeof(info->nsel_hist));
+  info->gpu_ms = c->last_ms;
+  info->seeded = h->seeded;
+  info->certified = h->certified;
+  info->leftovers = h->leftovers;
+}
+
+// CTAs of the cooperative launch: every slot the kernel can occupy (cached per context)
+static int fused_grid(Ctx* c) {
+  if (c->fz_grid != 0) return c->fz_grid;
+  int coop = 0, per_sm = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2m_fused_kernel, FZ_THREADS, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    c->fz_grid = -1;
+    return -1;
+  }
+  c->fz_grid = per_sm * c->sm_count;
+  return c->fz_grid;
+}
+
+// The whole loop as one persistent cooperative launch (s2m_fused.cuh).  dbg: per-point outputs of the last executed
+// iteration (device pointers), or null.
+static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                              int max_iter, liogpu_s2m_info* info, const SurfDebugOut* dbg) {
+  const int grid = fused_grid(c);
+  const int nchunks = div_up(n, FZ_THREADS);
+  FusedArgs A;
+  LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
+  LIOGPU_CUDA_OK(c, c->fz_rows.reserve(((size_t)nchunks + (size_t)grid) * S2M_SUMS * sizeof(double)));
+  LIOGPU_CUDA_OK(c, c->fz_left.reserve(((size_t)nchunks * FZ_THREADS + (size_t)nchunks + 64) * sizeof(int)));
+  LIOGPU_CUDA_OK(c, c->prev_nn.reserve((size_t)FZ_K * (size_t)n * sizeof(int)));
+  LIOGPU_CUDA_OK(c, c->fz_lb.reserve((size_t)n * sizeof(float)));
+  LIOGPU_CUDA_OK(c, c->hopeless.reserve((size_t)n * sizeof(float4)));
+  A.scan = scan4; A.nq = n;
+  A.map4 = c->map4.as<float4>(); A.map_sorted = c->map_sorted.as<float4>(); A.cell_start = c->cell_start.as<uint32_t>();
+  A.g = c->grid;
+  A.st = c->lm_state.as<LmDevState>();
+  A.chunk_rows = c->fz_rows.as<double>();
+  A.cta_rows = A.chunk_rows + (size_t)nchunks * S2M_SUMS;
+  A.left_list = c->fz_left.as<int>();
+  A.chunk_nleft = A.left_list + (size_t)nchunks * FZ_THREADS;
+  A.prev_nn = c->prev_nn.as<int>();
+  A.prev_lb = c->fz_lb.as<float>();
+  A.hopeless = c->hopeless.as<float4>();
+  A.probe = nullptr;
+  A.dbg = dbg ? *dbg : SurfDebugOut{nullptr, nullptr, nullptr, nullptr, nullptr};
+  A.nchunks = nchunks;
+  A.use_cert = c->prm.s2m_no_certificate ? 0 : 1;
+  const bool prof = c->prm.profile_kernels != 0;
+  unsigned long long* h_probe = reinterpret_cast<unsigned long long*>((char*)c->h_pinned + 8192);
+  if (prof) {
+    LIOGPU_CUDA_OK(c, c->fz_probe.reserve(LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long)));
+    A.probe = c->fz_probe.as<unsigned long long>();
+    LIOGPU_CUDA_OK(c, cudaMemsetAsync(A.probe, 0, LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long), c->stream));
+  }
+  LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
+  memset(h, 0, sizeof(LmDevState));
+  for (int k = 0; k < 6; ++k) h->pose[k] = pose_io[k];
+  for (int k = 0; k < 36; ++k) h->matP[k] = matP_io[k];
+  h->degenerate = *degenerate_io;
+  h->max_iter = max_iter;
+  LmDevState* d = A.st;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  void* kargs[] = {(void*)&A};
+  LIOGPU_CUDA_OK(c, cudaLaunchCooperativeKernel((const void*)s2m_fused_kernel, dim3((unsigned)grid), dim3(FZ_THREADS), kargs, 0, c->stream));
+  c->launches++;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(LmDevState), cudaMemcpyDeviceToHost, c->stream));
+  if (prof) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_probe, A.probe, LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  LIOGPU_CUDA_OK(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  for (int k = 0; k < 6; ++k) pose_io[k] = h->pose[k];
+  for (int k = 0; k < 36; ++k) matP_io[k] = h->matP[k];
+  *degenerate_io = h->degenerate;
+  if (info) {
+    fill_info(c, h, n, info);
+    info->kernel_launches = 1;
+    if (prof) {
+      double m = 0, l = 0, t = 0;
+      int cnt = 0;
+      for (int it = 0; it < LIOGPU_MAX_ITER; ++it) {
+        const unsigned long long* p = h_probe + it * 4;
+        if (!p[0] || !p[3]) break;
+        m += (double)(p[1] - p[0]); l += (double)(p[3] - p[1]); t += (double)(p[3] - p[2]);
+        ++cnt;
+      }
+      info->main_kernel_ms = (float)(m * 1e-6); info->left_kernel_ms = (float)(l * 1e-6); info->tail_ms = (float)(t * 1e-6);
+      info->main_kernel_launches = cnt; info->left_kernel_launches = cnt;
+    }
+  }
+  if (h->cert_mismatch) { c->err = "internal: eigen certificate contradicted by the exact computation"; return LIOGPU_E_INVALID; }
+  return LIOGPU_OK;
+}
+
+static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                               int max_iter, liogpu_s2m_info* info);
+
 int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
                  int max_iter, liogpu_s2m_info* info) {
   int rc = check_grid(c);
   if (rc != LIOGPU_OK) return rc;
   if (max_iter < 1 || max_iter > LIOGPU_MAX_ITER) { c->err = "max_iter out of range"; return LIOGPU_E_INVALID; }
+  // the fused loop keeps its chunk-offset table in shared memory: sweeps beyond 1,048,576 points (none of the
+  // reference's sensors) take the two-kernel path
+  if (c->prm.s2m_path == 0 && div_up(n, FZ_THREADS) <= FZ_MAXCHUNKS && fused_grid(c) > 1)
+    return scan2map_fused_dev(c, scan4, n, pose_io, matP_io, degenerate_io, max_iter, info, nullptr);
+  return scan2map_legacy_dev(c, scan4, n, pose_io, matP_io, degenerate_io, max_iter, info);
+}
+
+// One registration with the per-point results of its LAST executed iteration (parity tests of the fused loop).
+int scan2map_trace_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                       int max_iter, liogpu_s2m_info* info, int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag,
+                       unsigned char* tie) {
+  int rc = check_grid(c);
+  if (rc != LIOGPU_OK) return rc;
+  if (max_iter < 1 || max_iter > LIOGPU_MAX_ITER) { c->err = "max_iter out of range"; return LIOGPU_E_INVALID; }
+  if (div_up(n, FZ_THREADS) > FZ_MAXCHUNKS || fused_grid(c) <= 1) { c->err = "fused loop unavailable for this size / device"; return LIOGPU_E_INVALID; }
+  LIOGPU_CUDA_OK(c, c->dbg_idx.reserve((size_t)n * 5 * sizeof(int)));
+  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve((size_t)n * 5 * sizeof(float)));
+  LIOGPU_CUDA_OK(c, c->dbg_coeff.reserve((size_t)n * sizeof(float4)));
+  LIOGPU_CUDA_OK(c, c->dbg_flag.reserve((size_t)n));
+  LIOGPU_CUDA_OK(c, c->dbg_tie.reserve((size_t)n));
+  const SurfDebugOut dbg{c->dbg_idx.as<int>(), c->dbg_d2.as<float>(), c->dbg_coeff.as<float4>(),
+                         c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
+  rc = scan2map_fused_dev(c, scan4, n, pose_io, matP_io, degenerate_io, max_iter, info, &dbg);
+  if (rc != LIOGPU_OK) return rc;
+  if (nn_idx) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(nn_idx, dbg.nn_idx, (size_t)n * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (nn_d2) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(nn_d2, dbg.nn_d2, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (coeff) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(coeff, dbg.coeff, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (flag) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(flag, dbg.flag, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (tie) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(tie, dbg.tie, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return LIOGPU_OK;
+}
+
+static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float matP_io[36], int* degenerate_io,
+                               int max_iter, liogpu_s2m_info* info) {
+  int rc = LIOGPU_OK;
   S2mArgs A;
   int main_blocks = 0, left_blocks = 0;
   rc = prepare_args(c, scan4, n, A, main_blocks, left_blocks);
@@ -1235,6 +1386,7 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
   h->degenerate = *degenerate_io;
   h->max_iter = max_iter;
   LmDevState* d = A.st;
+  const unsigned long long launches_before = c->launches;
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   lm_prepare_kernel<<<1, 32, 0, c->stream>>>(d);
@@ -1295,20 +1447,8 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
   for (int k = 0; k < 36; ++k) matP_io[k] = h->matP[k];
   *degenerate_io = h->degenerate;
   if (info) {
-    info->iterations = h->iter;
-    info->converged = h->converged;
-    info->n_query = n;
-    info->n_sel = h->n_sel;
-    info->is_degenerate = h->degenerate;
-    info->tie_queries = h->tie_queries;
-    info->delta_r_deg = h->delta_r;
-    info->delta_t_cm = h->delta_t;
-    memcpy(info->JtJ, h->JtJ, sizeof(info->JtJ));
-    memcpy(info->Jtr, h->Jtr, sizeof(info->Jtr));
-    memcpy(info->pose_hist, h->pose_hist, sizeof(info->pose_hist));
-    memcpy(info->nsel_hist, h->nsel_hist, sizeof(info->nsel_hist));
-    info->gpu_ms = c->last_ms;
-    info->seeded = h->seeded;
+    fill_info(c, h, n, info);
+    info->kernel_launches = (int)(c->launches - launches_before);
     info->main_kernel_ms = prof_main_ms; info->left_kernel_ms = prof_left_ms;
     info->main_kernel_launches = prof_main_n; info->left_kernel_launches = prof_left_n;
   }
@@ -1367,4 +1507,4 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
 }
 
 }  // namespace liogpu
-static_assert(sizeof(liogpu::LmDevState) == 1616, "bench.py counts sizeof(LmDevState) bytes of H2D/D2H per registration");
+static_assert(sizeof(liogpu::LmDevState) == 1808, "bench.py counts sizeof(LmDevState) bytes of H2D/D2H per registration");

@@ -29,7 +29,8 @@ class Params(C.Structure):
                 ("downsample_rate", C.c_int), ("point_filter_num", C.c_int),
                 ("lidar_min_front", C.c_float), ("lidar_min_back", C.c_float), ("lidar_min_left", C.c_float),
                 ("lidar_min_right", C.c_float), ("lidar_max_range", C.c_float), ("lidar_max_intensity", C.c_float),
-                ("knn_cell_size", C.c_float), ("knn_phase1_radius", C.c_float), ("profile_kernels", C.c_int), ("reserved", C.c_int * 5)]
+                ("knn_cell_size", C.c_float), ("knn_phase1_radius", C.c_float), ("profile_kernels", C.c_int), ("s2m_path", C.c_int),
+                ("s2m_no_certificate", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class S2MInfo(C.Structure):
@@ -38,7 +39,8 @@ class S2MInfo(C.Structure):
                 ("delta_t_cm", C.c_float), ("JtJ", C.c_double * 36), ("Jtr", C.c_double * 6),
                 ("pose_hist", (C.c_float * 6) * LIOGPU_MAX_ITER), ("nsel_hist", C.c_int * LIOGPU_MAX_ITER),
                 ("gpu_ms", C.c_float), ("seeded", C.c_int), ("main_kernel_ms", C.c_float),
-                ("left_kernel_ms", C.c_float), ("main_kernel_launches", C.c_int), ("left_kernel_launches", C.c_int)]
+                ("left_kernel_ms", C.c_float), ("main_kernel_launches", C.c_int), ("left_kernel_launches", C.c_int),
+                ("certified", C.c_int), ("leftovers", C.c_int), ("tail_ms", C.c_float), ("kernel_launches", C.c_int)]
 
 
 class LocalMapParams(C.Structure):
@@ -72,7 +74,8 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
-           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext", "liogpu_extract_nearby"]
+           "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext", "liogpu_extract_nearby",
+           "liogpu_scan2map_trace"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -132,6 +135,9 @@ def load_library() -> C.CDLL:
                                              C.POINTER(C.c_int), C.POINTER(LocalMapInfo)]
     lib.liogpu_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo)]
+    lib.liogpu_scan2map_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
     lib.liogpu_downsample_scan2map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                C.POINTER(C.c_int), C.c_int, C.POINTER(S2MInfo), C.POINTER(C.c_int),
                                                C.c_void_p, C.c_int, C.c_int]
@@ -188,7 +194,9 @@ def info_to_dict(info: S2MInfo) -> dict:
                 pose_hist=np.array(info.pose_hist, dtype=np.float32).reshape(LIOGPU_MAX_ITER, 6)[:it],
                 nsel_hist=np.array(info.nsel_hist)[:it], gpu_ms=info.gpu_ms, seeded=info.seeded,
                 main_kernel_ms=info.main_kernel_ms, left_kernel_ms=info.left_kernel_ms,
-                main_kernel_launches=info.main_kernel_launches, left_kernel_launches=info.left_kernel_launches)
+                main_kernel_launches=info.main_kernel_launches, left_kernel_launches=info.left_kernel_launches,
+                certified=info.certified, leftovers=info.leftovers, tail_ms=info.tail_ms,
+                kernel_launches=info.kernel_launches)
 
 
 class LioGpu:
@@ -391,6 +399,26 @@ class LioGpu:
             d["status"] = st
             d["is_degenerate"] = deg.value
         return pose, P.reshape(6, 6), d
+
+    def scan2map_trace(self, scan_ds, pose6, matP=None, degenerate: int = 0, max_iter: int = 30):
+        """liogpu_scan2map plus the per-point results of its last executed iteration -> (pose, matP, info, per-point dict)."""
+        ptr, n, stride, keep = _cloud_args(scan_ds)
+        if isinstance(scan_ds, str) and scan_ds == RESIDENT:
+            n = self.resident_size()
+        pose = np.array(pose6, dtype=np.float32)
+        P = np.zeros(36, np.float32) if matP is None else np.array(matP, dtype=np.float32).reshape(36)
+        deg = C.c_int(int(degenerate))
+        info = S2MInfo()
+        idx = np.empty((n, 5), np.int32); d2 = np.empty((n, 5), np.float32)
+        coeff = np.empty((n, 4), np.float32); flag = np.empty(n, np.uint8); tie = np.empty(n, np.uint8)
+        st = self._check(self.lib.liogpu_scan2map_trace(self.h, ptr, n, stride, pose.ctypes.data, P.ctypes.data,
+                                                        C.byref(deg), max_iter, C.byref(info), idx.ctypes.data,
+                                                        d2.ctypes.data, coeff.ctypes.data, flag.ctypes.data,
+                                                        tie.ctypes.data))
+        d = info_to_dict(info)
+        d["status"] = st
+        d["is_degenerate"] = deg.value
+        return pose, P.reshape(6, 6), d, dict(nn_idx=idx, nn_d2=d2, coeff=coeff, flag=flag, tie=tie)
 
     def downsample_scan2map(self, scan, pose6, matP=None, degenerate: int = 0, max_iter: int = 30, fetch_ds=False,
                             keep_ds_on_device: bool = False):
