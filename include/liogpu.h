@@ -110,6 +110,11 @@ typedef struct liogpu_s2m_info {
   float tail_ms;     /* profile_kernels: summed time between a CTA's partial row and the release of
                         the next iteration (fixed-order reduction + 6x6 tail + barrier)            */
   int kernel_launches; /* kernels launched by this call                                            */
+  int certified_hist[LIOGPU_MAX_ITER]; /* per executed iteration: certified / seeded / leftover points      */
+  int seeded_hist[LIOGPU_MAX_ITER];
+  int leftover_hist[LIOGPU_MAX_ITER];
+  float main_us_hist[LIOGPU_MAX_ITER]; /* profile_kernels: search + plane-fit phase of every iteration, us   */
+  float rest_us_hist[LIOGPU_MAX_ITER]; /* profile_kernels: everything after it until the next iteration, us  */
 } liogpu_s2m_info;
 
 int liogpu_abi_version(void);
@@ -156,6 +161,32 @@ int liogpu_keyframe_count(const liogpu_ctx* ctx);
  * xyzi_out may be NULL; otherwise the voxelised map (laserCloudSurfFromMapDS) is copied out. */
 int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k,
                            float leaf, int* n_map, void* xyzi_out, int out_stride, int cap_out);
+
+/* ---- extractCloud with the VoxelGrid pass sharded by spatial tile over several GPUs (BASELINE configs[3]) ----
+ * Every GPU holds the keyframes (liogpu_keyframe_put on each context) and calls liogpu_voxel_tile with the same
+ * ids / poses / leaf and its own `tile` in [0, n_tiles).  The call transforms and concatenates the k keyframes like
+ * liogpu_build_local_map, plans the tiles ON THE DEVICE (coarse histogram of the voxel-row index (iz, iy), tile t =
+ * the rows between the t/N and (t+1)/N quantiles of the point count — the same plan on every GPU, nothing is
+ * exchanged), selects this tile's points in input order and voxelises them.  The tiles' outputs concatenated in tile
+ * order are bit-identical to the cloud liogpu_build_local_map produces (a voxel never spans two tiles and PCL's
+ * output order is lexicographic in (iz, iy, ix)); the caller gathers them (rank-ordered copies into disjoint slices,
+ * or an NCCL all-gather) and installs the result with liogpu_set_local_map.  xyzi_out may be a device pointer.
+ * On the overflow guard of the WHOLE cloud (q4) tile t returns the t-th contiguous slice of the input and the status
+ * is LIOGPU_W_LEAF_OVERFLOW, so the concatenation is again what PCL returns.  The registration's installed local
+ * map is left untouched. */
+typedef struct liogpu_tile_info {
+  int n_points;       /* points of the concatenated keyframes */
+  int n_rows;         /* voxel rows (iz, iy) of the whole cloud's bounding box */
+  int n_bins;         /* histogram bins the rows were grouped into (<= 65,536) */
+  int bin_lo, bin_hi; /* this tile's bin range [lo, hi) */
+  int n_tile_points;  /* points selected for this tile */
+  int leaf_overflow;
+  float gpu_ms;       /* device time of the call's kernels */
+  float plan_ms;      /* of which: transform + bounding box + histogram + bounds + selection */
+  int reserved[3];
+} liogpu_tile_info;
+int liogpu_voxel_tile(liogpu_ctx* ctx, const int* ids, const float* pose6s /* k*6 */, int k, float leaf, int tile,
+                      int n_tiles, void* xyzi_out, int out_stride, int cap_out, int* n_out, liogpu_tile_info* info);
 
 /* ---- publishLocalMap (MO:2442-2541), called after every registration (MO:504) ----
  * Filter settings of the node (utility.h:219-229, set up at MO:293-304). */

@@ -208,7 +208,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
-                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.fz_rows, &c.fz_left, &c.fz_lb, &c.fz_probe, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan,
+                    &c.fail_buf, &c.prev_nn, &c.hopeless, &c.fz_rows, &c.fz_left, &c.fz_lb, &c.fz_probe, &c.tile_plan, &c.tile_hist, &c.tile_pts, &c.tile_out, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie, &c.imu_tab, &c.dsk_flags, &c.dsk_scan,
                     &c.lm_flag, &c.lm_pos, &c.lm_a, &c.lm_b, &c.lm_md, &c.lm_left, &c.lm_out, &c.lm_stats, &c.sor_setup,
                     &c.sor_sorted, &c.sor_cell_start};
   for (DevBuf* b : bufs) b->release();
@@ -217,6 +217,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
   for (cudaEvent_t e : c.prof_ev) cudaEventDestroy(e);
+  if (c.ev_mid) cudaEventDestroy(c.ev_mid);
   if (c.ev_it0) cudaEventDestroy(c.ev_it0);
   if (c.ev_side) cudaEventDestroy(c.ev_side);
   if (c.side_stream) cudaStreamDestroy(c.side_stream);
@@ -399,6 +400,47 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   }
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
+}
+
+int liogpu_voxel_tile(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, int tile, int n_tiles,
+                      void* xyzi_out, int out_stride, int cap_out, int* n_out, liogpu_tile_info* info) {
+  int rc = enter(ctx);
+  if (rc) return rc;
+  Ctx* c = &ctx->c;
+  liogpu_tile_info local_info;
+  if (!info) info = &local_info;
+  std::memset(info, 0, sizeof(*info));
+  if (k < 0 || (k > 0 && (!ids || !pose6s)) || !n_out || n_tiles < 1 || tile < 0 || tile >= n_tiles || !(leaf > 0.f)) {
+    c->err = "liogpu_voxel_tile: bad arguments";
+    return LIOGPU_E_INVALID;
+  }
+  *n_out = 0;
+  KfTables t;
+  rc = stage_keyframes(c, "liogpu_voxel_tile", ids, pose6s, k, t);
+  if (rc) return rc;
+  if (t.total == 0) return LIOGPU_W_NO_KEYFRAMES;
+  const int total = (int)t.total;
+  if (!c->ev_mid) LIOGPU_CUDA_OK(c, cudaEventCreate(&c->ev_mid));
+  // scratch of publishLocalMap: the registration's local map / index and a resident sweep are not touched
+  LIOGPU_CUDA_OK(c, c->lm_a.reserve(t.total * sizeof(float4)));
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  LIOGPU_CUDA_OK(c, launch_transform_multi(c, t.srcs, t.offs, k, t.poses, t.T12, (long long)total, c->lm_a.as<float4>()));
+  int m = 0;
+  bool overflow = false;
+  rc = voxel_tile_dev(c, c->lm_a.as<float4>(), total, leaf, tile, n_tiles, c->tile_out, &m, &overflow, info);
+  if (rc) return rc;
+  LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+  *n_out = m;
+  if (xyzi_out && m > 0) {
+    if (m > cap_out) { c->err = "liogpu_voxel_tile: output capacity too small"; return LIOGPU_E_CAPACITY; }
+    rc = store_cloud(c, c->tile_out.as<float4>(), m, xyzi_out, out_stride);
+    if (rc) return rc;
+  }
+  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+  info->gpu_ms = c->last_ms;
+  cudaEventElapsedTime(&info->plan_ms, c->ev0, c->ev_mid);
   return overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
 }
 

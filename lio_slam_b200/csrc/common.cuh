@@ -88,12 +88,14 @@ struct LmDevState {
   int seeded;         // points of the last executed iteration that started from the previous neighbours
   // ---- fused persistent loop (s2m_fused.cuh); zeroed with the rest of the block at every registration ----
   float T_prev[12];   // transform of the previous iteration: where every point stood when its candidate set was certified
-  unsigned fz_barrier;                 // grid barrier counter (monotonic)
-  unsigned fz_ticket;                  // end-of-iteration ticket (monotonic)
-  unsigned fz_release;                 // iterations whose 6x6 tail has finished
-  unsigned fz_queue[LIOGPU_MAX_ITER];  // chunk queue head, one per iteration
+  unsigned fz_ticket_a[LIOGPU_MAX_ITER];  // CTAs that finished the main phase, per iteration
+  unsigned fz_ticket_b[LIOGPU_MAX_ITER];  // CTAs that finished the deferred-leftover phase, per iteration
+  unsigned fz_phase;                      // 2*it+1: iteration it needs the deferred-leftover phase; 2*it+2: iteration it done
+  unsigned fz_queue[LIOGPU_MAX_ITER];     // chunk queue head, one per iteration
+  unsigned fz_deferred[LIOGPU_MAX_ITER];  // leftovers deferred to the grid-wide phase, per iteration
   int certified;      // last executed iteration: points whose five neighbours came from the certificate (no grid walk)
   int leftovers;      // last executed iteration: points finished by the warp-cooperative full-gate search
+  int cert_hist[LIOGPU_MAX_ITER], left_hist[LIOGPU_MAX_ITER], seed_hist[LIOGPU_MAX_ITER];
   int pad_[1];
 };
 
@@ -126,6 +128,9 @@ struct Ctx {
   DevBuf vox_setup, grid_setup, minmax, lm_state, partials, block_counter, misc, fail_buf, prev_nn, hopeless;
   // fused persistent loop: per-chunk / per-CTA partial rows, leftover segments, candidate-set bounds, probes
   DevBuf fz_rows, fz_left, fz_lb, fz_probe;
+  // tile-sharded rebuild (tile.cu)
+  DevBuf tile_plan, tile_hist, tile_pts, tile_out;
+  cudaEvent_t ev_mid = nullptr;
   int fz_grid = 0;        // CTAs of the cooperative launch (0 = not yet queried, < 0 = unavailable)
   // per-point debug outputs of surf_optimization
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
@@ -166,6 +171,9 @@ cudaError_t exclusive_scan_u32(Ctx* c, const uint32_t* in, uint32_t* out, int n,
 // --- voxel.cu
 cudaError_t launch_minmax(Ctx* c, const float4* pts, int n, unsigned* mm);
 int voxel_downsample_dev(Ctx* c, const float4* in, int n, float leaf, DevBuf& out, int* n_out, bool* overflow);
+// --- tile.cu
+int voxel_tile_dev(Ctx* c, const float4* pts, int n, float leaf, int tile, int n_tiles, DevBuf& out, int* n_out,
+                   bool* overflow, liogpu_tile_info* info);
 // --- grid.cu
 int grid_build_dev(Ctx* c, const float4* map4, int n, float leaf_hint);
 int grid_build_core(Ctx* c, const float4* pts, int n, float cell, float gate_d2, float gate1_d2, DevBuf& setup,

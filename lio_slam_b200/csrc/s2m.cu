@@ -1287,9 +1287,9 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
   const bool prof = c->prm.profile_kernels != 0;
   unsigned long long* h_probe = reinterpret_cast<unsigned long long*>((char*)c->h_pinned + 8192);
   if (prof) {
-    LIOGPU_CUDA_OK(c, c->fz_probe.reserve(LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long)));
+    LIOGPU_CUDA_OK(c, c->fz_probe.reserve(LIOGPU_MAX_ITER * FZ_PROBES * sizeof(unsigned long long)));
     A.probe = c->fz_probe.as<unsigned long long>();
-    LIOGPU_CUDA_OK(c, cudaMemsetAsync(A.probe, 0, LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long), c->stream));
+    LIOGPU_CUDA_OK(c, cudaMemsetAsync(A.probe, 0, LIOGPU_MAX_ITER * FZ_PROBES * sizeof(unsigned long long), c->stream));
   }
   LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
   memset(h, 0, sizeof(LmDevState));
@@ -1305,7 +1305,7 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
   c->launches++;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h, d, sizeof(LmDevState), cudaMemcpyDeviceToHost, c->stream));
-  if (prof) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_probe, A.probe, LIOGPU_MAX_ITER * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  if (prof) LIOGPU_CUDA_OK(c, cudaMemcpyAsync(h_probe, A.probe, LIOGPU_MAX_ITER * FZ_PROBES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));
   LIOGPU_CUDA_OK(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   for (int k = 0; k < 6; ++k) pose_io[k] = h->pose[k];
@@ -1314,13 +1314,22 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
   if (info) {
     fill_info(c, h, n, info);
     info->kernel_launches = 1;
+    for (int it = 0; it < LIOGPU_MAX_ITER; ++it) {
+      info->certified_hist[it] = h->cert_hist[it]; info->seeded_hist[it] = h->seed_hist[it];
+      info->leftover_hist[it] = h->left_hist[it];
+    }
     if (prof) {
+      // probes (ns, %globaltimer): 0 iteration start, 2 last CTA out of the main phase, 5 last CTA out of the
+      // deferred-leftover phase (if it ran), 6 sums complete, 7 6x6 tail done
       double m = 0, l = 0, t = 0;
       int cnt = 0;
-      for (int it = 0; it < LIOGPU_MAX_ITER; ++it) {
-        const unsigned long long* p = h_probe + it * 4;
-        if (!p[0] || !p[3]) break;
-        m += (double)(p[1] - p[0]); l += (double)(p[3] - p[1]); t += (double)(p[3] - p[2]);
+      for (int it = 0; it < h->iter && it < LIOGPU_MAX_ITER; ++it) {
+        const unsigned long long* p = h_probe + it * FZ_PROBES;
+        if (!p[0] || !p[2] || !p[7]) break;
+        const unsigned long long arrive = p[5] ? p[5] : p[2];
+        m += (double)(p[2] - p[0]); l += (double)(p[7] - p[2]); t += (double)(p[7] - arrive);
+        info->main_us_hist[it] = (float)((double)(p[2] - p[0]) * 1e-3);
+        info->rest_us_hist[it] = (float)((double)(p[7] - p[2]) * 1e-3);
         ++cnt;
       }
       info->main_kernel_ms = (float)(m * 1e-6); info->left_kernel_ms = (float)(l * 1e-6); info->tail_ms = (float)(t * 1e-6);
@@ -1507,4 +1516,4 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
 }
 
 }  // namespace liogpu
-static_assert(sizeof(liogpu::LmDevState) == 1808, "bench.py counts sizeof(LmDevState) bytes of H2D/D2H per registration");
+static_assert(sizeof(liogpu::LmDevState) == 2520, "bench.py counts sizeof(LmDevState) bytes of H2D/D2H per registration");

@@ -22,11 +22,15 @@
 //                                chunk's segment of the leftover list.
 //                    3 fit       thread = point: 5x3 plane fit, weight, Jacobian row; FP64 block reduction of the
 //                                27 sums of A^T A / A^T b into the chunk's partial row.
-//     grid barrier
-//     leftovers    warp-cooperative full-gate search (one point per warp, static map -> fixed summation order),
-//                  fold of the chunk rows, per-CTA partial row
-//     ticket       the last CTA to arrive adds the CTA rows in a fixed order and runs the 6x6 tail of LMOptimization
-//                  (lm_finalize_warp), then releases the others (second grid barrier)
+//                  A chunk with at most 8 such points finishes them on the spot (one warp-cooperative full-gate search
+//                  per warp); a chunk with more defers them to the grid-wide leftover phase.
+//     ticket A     the last CTA to finish the main phase looks at the number of deferred leftovers:
+//                    none (the usual case from iteration 1 on): it adds the chunk rows in a fixed order, runs the
+//                          6x6 tail of LMOptimization (lm_finalize_warp) and releases the others — ONE grid-wide
+//                          synchronisation per iteration;
+//                    some: it opens the leftover phase: warp-cooperative full-gate search, one point per warp over
+//                          the whole grid (static map -> fixed summation order), per-CTA partial rows, ticket B, the
+//                          last CTA adds chunk rows + CTA rows, runs the tail and releases the others.
 //
 // Nothing returns to the host inside the loop; the 1.8 KB state block is read back once.
 #pragma once
@@ -42,6 +46,9 @@ constexpr int FZ_K = LIOGPU_FZ_K;        // members of a candidate set
 constexpr int FZ_MAXCHUNKS = 4096;       // chunk-offset table of the leftover phase lives in shared memory
 constexpr float FZ_REL = 1e-5f;          // relative safety margin of every bound (f32 rounding is < 3e-7)
 constexpr float FZ_SEED_MARGIN = 0.10f;  // a seeded search enumerates this far (m) beyond the seeds' 5th distance
+constexpr int FZ_DIRECT_MIN = 128;       // chunks with more search requests than this skip the compaction (thread = point)
+constexpr int FZ_INPLACE = FZ_WARPS;     // chunks with at most this many leftovers finish them on the spot
+constexpr int FZ_PROBES = 8;             // %globaltimer stamps per iteration (profile_kernels)
 
 // ---- 9 best (d2, map index) pairs, same 64-bit keys as Top5; slot FZ_K is the pruning threshold ----
 struct TopN {
@@ -149,7 +156,7 @@ struct FusedArgs {
   int* prev_nn;            // [FZ_K][nq] candidate set of every point (-1: empty slot; prev_nn[0][i] < 0: no set)
   float* prev_lb;          // [nq] lower bound on the distance to every map point outside the set
   float4* hopeless;        // [nq] see HOPELESS_MARGIN
-  unsigned long long* probe;  // [LIOGPU_MAX_ITER][4] %globaltimer stamps of CTA 0 (profile_kernels), or null
+  unsigned long long* probe;  // [LIOGPU_MAX_ITER][FZ_PROBES] %globaltimer stamps (profile_kernels), or null
   SurfDebugOut dbg;        // per-point outputs of the last executed iteration (trace entry point), or nulls
   int nchunks;
   int use_cert;            // 0: never take the certificate (A/B switch: every point with a set is searched)
@@ -166,17 +173,6 @@ __device__ __forceinline__ unsigned fz_ld_acquire(const unsigned* p) {
   return v;
 }
 
-// grid barrier over the compute CTAs: monotonic counter, target = (number of barriers so far) x CTAs
-__device__ __forceinline__ void fz_grid_barrier(unsigned* counter, const unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (fz_ld_acquire(counter) < target) { }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 // transPointAssociateToMap + LM trig of `pose` into caller storage (same arithmetic as warp_refresh_transform)
 __device__ __forceinline__ void fz_warp_transform(const int lane, const float pose_l, float* T, float* trig) {
@@ -234,10 +230,11 @@ __device__ __forceinline__ void fz_matp_warp(LmDevState* st, FinSmem& m, const i
 // shared-memory carve-up: the main phase and the leftover phase never overlap in time
 struct FzMainSmem {
   int res_id[5][FZ_THREADS];      // the five neighbours of every slot of the chunk
-  float bound[FZ_THREADS];        // search request: > 0 seeded bound, 0 phase-1 gate, < 0 straight to the leftovers
+  float bound[FZ_THREADS];        // search request: > 0 seeded bound, 0 phase-1 gate, -1 straight to the leftovers, -2 none
   float rows[FZ_THREADS][8];      // Jacobian row, rhs, accepted flag
   unsigned char res_meta[FZ_THREADS];  // bit0 found, bit1 tie
   unsigned char list[FZ_THREADS];      // slots queued for the search step, slot order
+  unsigned char llist[FZ_THREADS];     // slots the search could not settle (leftovers), list order
 };
 struct FzLeftSmem {
   int off[FZ_MAXCHUNKS + 1];
@@ -248,12 +245,57 @@ union FzSmem {
   FzLeftSmem l;
 };
 
+// what a leftover search leaves behind for the next iteration: the candidate set (its five neighbours), the bound
+// (everything else it visited was >= rej away, everything it did not visit is beyond the extended gate) and the
+// hopeless marker
+__device__ __forceinline__ void fz_store_leftover(const FusedArgs& A, const int mine, const float4 sel, const Top5& t,
+                                                  const int n_ext, const float ge2, const bool found) {
+  A.prev_nn[mine] = found ? t.i(t.k0) : -1;
+  A.prev_nn[(size_t)A.nq + mine] = t.i(t.k1);
+  A.prev_nn[2 * (size_t)A.nq + mine] = t.i(t.k2);
+  A.prev_nn[3 * (size_t)A.nq + mine] = t.i(t.k3);
+  A.prev_nn[4 * (size_t)A.nq + mine] = t.i(t.k4);
+#pragma unroll
+  for (int j = 5; j < FZ_K; ++j) A.prev_nn[(size_t)j * A.nq + mine] = -1;
+  A.prev_lb[mine] = sqrtf(fminf(t.rej, ge2)) * (1.f - FZ_REL);
+  const bool hopeless = !found && n_ext < 5;
+  A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, hopeless ? 1.f : 0.f);
+}
+
+// sum of `nrows` partial rows (S2M_SUMS doubles each) in a fixed order: warp w takes rows w, w+8, ... with eight
+// independent accumulators (eight 256-byte loads in flight per warp), then the warps are added in order.
+// Result: lane l of warp 0 returns sum[l]; every thread must call it.
+__device__ __forceinline__ double fz_reduce_rows(const double* __restrict__ rows, const int nrows, double (*red)[S2M_SUMS],
+                                                 const int warp, const int lane) {
+  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  constexpr int W = FZ_WARPS;
+  int b = warp;
+  for (; b + 7 * W < nrows; b += 8 * W) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldcg(rows + (size_t)(b + k * W) * S2M_SUMS + lane);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += v[k];
+  }
+  for (int k = 0; b < nrows; b += W, ++k) a[k] += __ldcg(rows + (size_t)b * S2M_SUMS + lane);
+  __syncthreads();
+  red[warp][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  double sum = 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < FZ_WARPS; ++k) sum += red[k][lane];
+  }
+  return sum;
+}
+
 __global__ void __launch_bounds__(FZ_THREADS, FZ_MINBLOCKS_CFG)
 s2m_fused_kernel(const FusedArgs A) {
   __shared__ float sT[12], sTp[12];
   __shared__ LmTrig sTrig;
   __shared__ __align__(16) FzSmem sm;
   __shared__ double red[FZ_WARPS][S2M_SUMS];
+  __shared__ double s_sum[S2M_SUMS];
   __shared__ FinSmem s_fin;
   __shared__ int s_chunk, s_wcnt[FZ_WARPS], s_wcnt2[FZ_WARPS], s_misc[4];
   __shared__ bool s_last;
@@ -264,7 +306,7 @@ s2m_fused_kernel(const FusedArgs A) {
   if ((int)blockIdx.x == G) {
     // ---- service CTA: iteration 0's eigen-decomposition + matP while iterations 1.. run ----
     if (tid < 32) {
-      if (lane == 0) { while (fz_ld_acquire(&st->fz_release) < 1u) { } __threadfence(); }
+      if (lane == 0) { while (fz_ld_acquire(&st->fz_phase) < 2u) { } __threadfence(); }
       __syncwarp();
       if (__ldcg(&st->eig_pending)) fz_matp_warp(st, s_fin, lane);
     }
@@ -273,16 +315,17 @@ s2m_fused_kernel(const FusedArgs A) {
 
   const bool can_phase1 = A.g.gate1_d2 < A.g.gate_d2;  // dense map: cheap first phase inside a small gate
   const int max_iter = st->max_iter;
-  unsigned bar_target = 0;
   const RowAcc ra = row_acc_of(lane);
+  const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;  // extended gate of the leftover search
+  const float ge2 = ge * ge;
 
   for (int it = 0; it < max_iter; ++it) {
+    unsigned long long* const probe = A.probe ? A.probe + it * FZ_PROBES : nullptr;
     // ---- this iteration's transform (updatePointAssociateToMap, :1613-1616) ----
     if (it == 0) {
       if (tid < 32) {
         const float pose_l = lane < 6 ? st->pose[lane] : 0.f;
-        float* trig = &sTrig.srx;
-        fz_warp_transform(lane, pose_l, sT, trig);
+        fz_warp_transform(lane, pose_l, sT, &sTrig.srx);
       }
     } else {
       if (tid < 12) { sT[tid] = __ldcg(st->T + tid); sTp[tid] = __ldcg(st->T_prev + tid); }
@@ -292,7 +335,8 @@ s2m_fused_kernel(const FusedArgs A) {
       }
     }
     __syncthreads();
-    if (A.probe && blockIdx.x == 0 && tid == 0) A.probe[it * 4 + 0] = fz_globaltimer();
+    if (probe && blockIdx.x == 0 && tid == 0) probe[0] = fz_globaltimer();
+    int cta_deferred = 0;  // meaningful in thread 0
 
     // =========================== main phase: dynamic queue of 256-point chunks ===========================
     for (;;) {
@@ -303,7 +347,7 @@ s2m_fused_kernel(const FusedArgs A) {
       const int base = c * FZ_THREADS;
       const int i = base + tid;
       // ---- step 1: classify ----
-      float req = -2.f;          // -2: no search request
+      float req = -2.f;
       int n_seeded = 0, n_cert = 0;
       unsigned char meta = 0;
       if (i < A.nq) {
@@ -351,7 +395,7 @@ s2m_fused_kernel(const FusedArgs A) {
                 for (int j = 0; j < 5; ++j) sm.m.res_id[j][tid] = (int)(unsigned)(key[j] & 0xffffffffull);
                 const float d0 = __uint_as_float((unsigned)(key[0] >> 32)), d1 = __uint_as_float((unsigned)(key[1] >> 32));
                 const float d2 = __uint_as_float((unsigned)(key[2] >> 32)), d3 = __uint_as_float((unsigned)(key[3] >> 32));
-                const float d5 = __uint_as_float((unsigned)(key[5] >> 32));  // 6th of the set (NaN pattern if empty: never equal)
+                const float d5 = __uint_as_float((unsigned)(key[5] >> 32));
                 const bool tie = d0 == d1 || d1 == d2 || d2 == d3 || d3 == D5 || (key[5] != ~0ull && D5 == d5);
                 meta = (unsigned char)(1 | (tie ? 2 : 0));
                 A.prev_lb[i] = L * (1.f - FZ_REL);
@@ -362,25 +406,27 @@ s2m_fused_kernel(const FusedArgs A) {
       }
       sm.m.res_meta[tid] = meta;
       sm.m.bound[tid] = req;
-      // queue the search requests in slot order
       const bool want = req > -2.f;
       const unsigned wm = __ballot_sync(FULL, want);
       if (lane == 0) s_wcnt[warp] = __popc(wm);
       __syncthreads();
-      int ns = 0;
-      {
-        int off = 0;
+      int ns = 0, woff = 0;
 #pragma unroll
-        for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) off += s_wcnt[w]; ns += s_wcnt[w]; }
-        if (want) sm.m.list[off + __popc(wm & ((1u << lane) - 1u))] = (unsigned char)tid;
+      for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) woff += s_wcnt[w]; ns += s_wcnt[w]; }
+      // search-heavy chunk (iterations 0 and 1): thread = point, no compaction; otherwise the requests are
+      // compacted so that the searching warps run with dense lanes
+      const bool direct = ns > FZ_DIRECT_MIN;
+      if (!direct) {
+        if (want) sm.m.list[woff + __popc(wm & ((1u << lane) - 1u))] = (unsigned char)tid;
+        __syncthreads();
       }
-      __syncthreads();
-      // ---- step 2: search (dense over the queued slots) ----
+      // ---- step 2: search ----
       bool need2 = false;
-      int qi = -1;
-      if (tid < ns) {
-        const int slot = sm.m.list[tid];
-        qi = base + slot;
+      int slot = -1;
+      if (direct) { if (want) slot = tid; }
+      else if (tid < ns) slot = sm.m.list[tid];
+      if (slot >= 0) {
+        const int qi = base + slot;
         const float rq = sm.m.bound[slot];
         need2 = true;
         if (rq >= 0.f) {
@@ -408,16 +454,45 @@ s2m_fused_kernel(const FusedArgs A) {
           }
         }
       }
-      {  // leftovers of this chunk, in list order
+      // leftovers of this chunk, in search order
+      int nl = 0;
+      {
         const unsigned fm = __ballot_sync(FULL, need2);
         if (lane == 0) s_wcnt2[warp] = __popc(fm);
         __syncthreads();
-        int off = 0, tot = 0;
+        int off = 0;
 #pragma unroll
-        for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) off += s_wcnt2[w]; tot += s_wcnt2[w]; }
-        if (need2) A.left_list[(size_t)base + off + __popc(fm & ((1u << lane) - 1u))] = qi;
-        if (tid == 0) A.chunk_nleft[c] = tot;
+        for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) off += s_wcnt2[w]; nl += s_wcnt2[w]; }
+        if (need2) sm.m.llist[off + __popc(fm & ((1u << lane) - 1u))] = (unsigned char)slot;
       }
+      const bool deferred = nl > FZ_INPLACE;
+      if (nl > 0) {
+        __syncthreads();
+        if (!deferred) {
+          // a handful: one warp-cooperative full-gate search per warp, right here
+          if (warp < nl) {
+            const int ls = sm.m.llist[warp];
+            const int mine = base + ls;
+            const float4 sel = apply_T(sT, A.scan[mine]);
+            Top5 t;
+            const int n_ext = warp_knn5(sel, A.g, ge2, A.map_sorted, A.cell_start, lane, t);
+            if (lane == 0) {
+              const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641
+              fz_store_leftover(A, mine, sel, t, n_ext, ge2, found);
+              if (found) {
+                sm.m.res_id[0][ls] = t.i(t.k0); sm.m.res_id[1][ls] = t.i(t.k1); sm.m.res_id[2][ls] = t.i(t.k2);
+                sm.m.res_id[3][ls] = t.i(t.k3); sm.m.res_id[4][ls] = t.i(t.k4);
+                sm.m.res_meta[ls] = (unsigned char)(1 | (t.tie() ? 2 : 0));
+              }
+            }
+          }
+        } else {
+          if (tid < nl) A.left_list[(size_t)base + tid] = base + sm.m.llist[tid];
+          if (tid == 0) cta_deferred += nl;
+        }
+      }
+      if (tid == 0) A.chunk_nleft[c] = deferred ? nl : 0;
+      __syncthreads();
       // ---- step 3: plane fit + Jacobian row (thread = point) ----
       float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float rhs = 0.f;
@@ -427,7 +502,7 @@ s2m_fused_kernel(const FusedArgs A) {
         float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
         int nid[5] = {-1, -1, -1, -1, -1};
         float nd2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        const bool pending = sm.m.bound[tid] > -2.f && !(mt & 1);  // went to the leftover list: finished there
+        const bool pending = deferred && sm.m.bound[tid] > -2.f && !(mt & 1);  // finished by the leftover phase
         if (mt & 1) {
           const float4 ori = A.scan[i];
           const float4 sel = apply_T(sT, ori);
@@ -451,7 +526,6 @@ s2m_fused_kernel(const FusedArgs A) {
           if (A.dbg.tie) A.dbg.tie[i] = tie ? 1 : 0;
         }
       }
-      __syncthreads();  // res_* / bound / list are dead from here; rows aliases nothing of them (distinct members)
 #pragma unroll
       for (int k = 0; k < 6; ++k) sm.m.rows[tid][k] = row[k];
       sm.m.rows[tid][6] = rhs;
@@ -472,6 +546,7 @@ s2m_fused_kernel(const FusedArgs A) {
         if (lane == 28) acc = (double)w_ties;
         if (lane == 29) acc = (double)w_seed;
         if (lane == 30) acc = (double)w_cert;
+        if (lane == 31) acc = warp == 0 ? (double)nl : 0.0;
         red[warp][lane] = acc;
       }
       __syncthreads();
@@ -484,205 +559,222 @@ s2m_fused_kernel(const FusedArgs A) {
       __syncthreads();
     }
 
-    // =========================== grid barrier: every chunk row and leftover segment is complete ===========================
-    bar_target += (unsigned)G;
-    fz_grid_barrier(&st->fz_barrier, bar_target);
-    if (A.probe && blockIdx.x == 0 && tid == 0) A.probe[it * 4 + 1] = fz_globaltimer();
-
-    // =========================== leftover phase ===========================
-    {
-      // exclusive scan of the per-chunk leftover counts (every CTA builds its own copy: no extra barrier)
-      constexpr int PER = FZ_MAXCHUNKS / FZ_THREADS;  // 16
-      int cnt[PER];
-      int local = 0;
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int cidx = tid * PER + k;
-        cnt[k] = cidx < A.nchunks ? __ldcg(A.chunk_nleft + cidx) : 0;
-        local += cnt[k];
-      }
-      int incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s_wcnt[warp] = incl;
-      __syncthreads();
-      int run = incl - local;
-      for (int w = 0; w < warp; ++w) run += s_wcnt[w];
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int cidx = tid * PER + k;
-        if (cidx < A.nchunks) sm.l.off[cidx] = run;
-        run += cnt[k];
-      }
-      if (tid == FZ_THREADS - 1) s_misc[0] = run;
-      __syncthreads();
-      if (tid == 0) sm.l.off[A.nchunks] = s_misc[0];
-      __syncthreads();
+    // =========================== ticket A: the last CTA out of the main phase decides ===========================
+    if (probe && blockIdx.x == 0 && tid == 0) probe[1] = fz_globaltimer();
+    if (tid == 0) {
+      if (cta_deferred) atomicAdd(&st->fz_deferred[it], (unsigned)cta_deferred);
+      __threadfence();
+      s_last = (atomicAdd(&st->fz_ticket_a[it], 1u) == (unsigned)(G - 1));
     }
-    const int total = s_misc[0];
-    const int warps_per_grid = G * FZ_WARPS;
-    const int per_warp = min(32, max(1, (total + warps_per_grid - 1) / warps_per_grid));
-    const int nbatch = (total + per_warp - 1) / per_warp;
-    double acc = 0.0;
-    int ties = 0;
-    for (int r0 = 0; r0 < nbatch; r0 += warps_per_grid) {
-      const int batch = r0 + (int)blockIdx.x * FZ_WARPS + warp;
-      float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float rhs = 0.f;
-      bool flag = false, tie = false;
-      if (batch < nbatch) {
-        const int e0 = batch * per_warp;
-        const int cnt = min(per_warp, total - e0);
-        int mine = -1;
-        if (lane < cnt) {
-          const int e = e0 + lane;
-          int lo = 0, hi = A.nchunks;  // invariant: off[lo] <= e < off[hi]
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sm.l.off[mid] <= e) lo = mid; else hi = mid;
-          }
-          mine = __ldcg(A.left_list + (size_t)lo * FZ_THREADS + (e - sm.l.off[lo]));
-        }
-        float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
-        if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
-        Top5 t;
-        t.init(A.g.gate_d2);
-        int my_ext = 0;
-        const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;
-        for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
-          float4 q;
-          q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j);
-          q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
-          Top5 tj;
-          const int n_ext = warp_knn5(q, A.g, ge * ge, A.map_sorted, A.cell_start, lane, tj);
-          if (lane == j) { t = tj; my_ext = n_ext; }
-        }
-        if (mine >= 0) {
-          const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641
-          float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 nbr[5];
-          if (found) {
-            nbr[0] = __ldg(A.map4 + t.i(t.k0)); nbr[1] = __ldg(A.map4 + t.i(t.k1)); nbr[2] = __ldg(A.map4 + t.i(t.k2));
-            nbr[3] = __ldg(A.map4 + t.i(t.k3)); nbr[4] = __ldg(A.map4 + t.i(t.k4));
-            flag = plane_residual(ori, sel, nbr, coeff);
-            tie = t.tie();
-            if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (flag) jacobian_row(sTrig, ori, coeff, row, rhs);
-          // candidate set of a leftover: its five neighbours; everything else it visited was >= rej away and
-          // everything it did not visit is beyond the extended gate
-          A.prev_nn[mine] = found ? t.i(t.k0) : -1;
-          A.prev_nn[(size_t)A.nq + mine] = t.i(t.k1);
-          A.prev_nn[2 * (size_t)A.nq + mine] = t.i(t.k2);
-          A.prev_nn[3 * (size_t)A.nq + mine] = t.i(t.k3);
-          A.prev_nn[4 * (size_t)A.nq + mine] = t.i(t.k4);
-#pragma unroll
-          for (int j = 5; j < FZ_K; ++j) A.prev_nn[(size_t)j * A.nq + mine] = -1;
-          A.prev_lb[mine] = sqrtf(fminf(t.rej, ge * ge)) * (1.f - FZ_REL);
-          const bool hopeless = !found && my_ext < 5;
-          A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, hopeless ? 1.f : 0.f);
-          if (A.dbg.nn_idx) {
-            int* o = A.dbg.nn_idx + (size_t)mine * 5;
-            o[0] = found ? t.i(t.k0) : -1; o[1] = found ? t.i(t.k1) : -1; o[2] = found ? t.i(t.k2) : -1;
-            o[3] = found ? t.i(t.k3) : -1; o[4] = found ? t.i(t.k4) : -1;
-          }
-          if (A.dbg.nn_d2) {
-            float* o = A.dbg.nn_d2 + (size_t)mine * 5;
-            o[0] = t.d(t.k0); o[1] = t.d(t.k1); o[2] = t.d(t.k2); o[3] = t.d(t.k3); o[4] = t.d(t.k4);
-          }
-          if (A.dbg.coeff) A.dbg.coeff[mine] = coeff;
-          if (A.dbg.flag) A.dbg.flag[mine] = flag ? 1 : 0;
-          if (A.dbg.tie) A.dbg.tie[mine] = tie ? 1 : 0;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) sm.l.rows[tid][k] = row[k];
-      sm.l.rows[tid][6] = rhs;
-      sm.l.rows[tid][7] = flag ? 1.f : 0.f;
-      if (flag && tie) ++ties;
-      __syncwarp();
-      if (ra.live) {  // every warp owns the slice of rows its own lanes staged
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const float* rr = sm.l.rows[warp * 32 + r];
-          acc += (double)rr[ra.a] * (double)rr[ra.b];
-        }
-      }
-      __syncwarp();
-    }
-    // fold this warp's share of the chunk rows (static map: fixed order of additions)
-    {
-      const int gw = (int)blockIdx.x * FZ_WARPS + warp;
-#pragma unroll 4
-      for (int b = gw; b < A.nchunks; b += warps_per_grid) acc += __ldcg(A.chunk_rows + (size_t)b * S2M_SUMS + lane);
-    }
-    {
-      int wt = ties;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
-      if (lane == 28) acc += (double)wt;
-    }
-    red[warp][lane] = acc;
     __syncthreads();
-    if (tid < S2M_SUMS) {
-      double sum = 0.0;
-#pragma unroll
-      for (int k = 0; k < FZ_WARPS; ++k) sum += red[k][tid];
-      A.cta_rows[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
-    }
-    if (A.probe && blockIdx.x == 0 && tid == 0) A.probe[it * 4 + 2] = fz_globaltimer();
-    // =========================== ticket: the last CTA reduces and runs the 6x6 tail ===========================
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&st->fz_ticket, 1u) == (unsigned)((it + 1) * G - 1));
-    __syncthreads();
+    bool left_phase = false;
     if (s_last) {
       __threadfence();
-      {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        constexpr int W = FZ_WARPS;
-        int b = warp;
-        for (; b + 3 * W < G; b += 4 * W) {
-          const double v0 = __ldcg(A.cta_rows + (size_t)b * S2M_SUMS + lane);
-          const double v1 = __ldcg(A.cta_rows + (size_t)(b + W) * S2M_SUMS + lane);
-          const double v2 = __ldcg(A.cta_rows + (size_t)(b + 2 * W) * S2M_SUMS + lane);
-          const double v3 = __ldcg(A.cta_rows + (size_t)(b + 3 * W) * S2M_SUMS + lane);
-          a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-        }
-        for (; b < G; b += W) a0 += __ldcg(A.cta_rows + (size_t)b * S2M_SUMS + lane);
-        red[warp][lane] = (a0 + a1) + (a2 + a3);
+      if (tid == 0) {
+        s_misc[2] = (int)__ldcg(&st->fz_deferred[it]);
+        if (probe) probe[2] = fz_globaltimer();
       }
+      __syncthreads();
+      left_phase = s_misc[2] > 0;
+      if (left_phase) {
+        if (tid == 0) { __threadfence(); atomicExch(&st->fz_phase, (unsigned)(2 * it + 1)); }
+      } else {
+        const double sum = fz_reduce_rows(A.chunk_rows, A.nchunks, red, warp, lane);
+        if (tid < S2M_SUMS) s_sum[tid] = sum;
+        if (probe && tid == 0) probe[6] = fz_globaltimer();
+        __syncthreads();
+        if (tid < 32) {
+          if (tid < 12) st->T_prev[tid] = sT[tid];  // where the points stood in this iteration
+          if (tid == 0) {
+            st->certified = (int)s_sum[30]; st->leftovers = (int)s_sum[31];
+            st->cert_hist[it] = (int)s_sum[30]; st->left_hist[it] = (int)s_sum[31]; st->seed_hist[it] = (int)s_sum[29];
+          }
+          __syncwarp();
+          lm_finalize_warp(st, s_sum, s_fin, tid);
+          __syncwarp();
+          if (tid == 0) {
+            if (probe) probe[7] = fz_globaltimer();
+            __threadfence();
+            atomicExch(&st->fz_phase, (unsigned)(2 * it + 2));
+          }
+        }
+      }
+    }
+    // everybody: wait for the decision
+    if (tid == 0) {
+      unsigned ph;
+      while ((ph = fz_ld_acquire(&st->fz_phase)) < (unsigned)(2 * it + 1)) { }
+      __threadfence();
+      s_misc[3] = (int)ph;
+    }
+    __syncthreads();
+
+    if (s_misc[3] == 2 * it + 1) {
+      // =========================== deferred-leftover phase (whole grid) ===========================
+      {
+        // exclusive scan of the per-chunk deferred counts (every CTA builds its own copy)
+        constexpr int PER = FZ_MAXCHUNKS / FZ_THREADS;  // 16
+        int cnt[PER];
+        int local = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int cidx = tid * PER + k;
+          cnt[k] = cidx < A.nchunks ? __ldcg(A.chunk_nleft + cidx) : 0;
+          local += cnt[k];
+        }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        __syncthreads();
+        int run = incl - local;
+        for (int w = 0; w < warp; ++w) run += s_wcnt[w];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int cidx = tid * PER + k;
+          if (cidx < A.nchunks) sm.l.off[cidx] = run;
+          run += cnt[k];
+        }
+        if (tid == FZ_THREADS - 1) s_misc[0] = run;
+        __syncthreads();
+        if (tid == 0) sm.l.off[A.nchunks] = s_misc[0];
+        __syncthreads();
+      }
+      const int total = s_misc[0];
+      const int warps_per_grid = G * FZ_WARPS;
+      const int per_warp = min(32, max(1, (total + warps_per_grid - 1) / warps_per_grid));
+      const int nbatch = (total + per_warp - 1) / per_warp;
+      double acc = 0.0;
+      int ties = 0;
+      for (int r0 = 0; r0 < nbatch; r0 += warps_per_grid) {
+        const int batch = r0 + (int)blockIdx.x * FZ_WARPS + warp;
+        float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float rhs = 0.f;
+        bool flag = false, tie = false;
+        if (batch < nbatch) {
+          const int e0 = batch * per_warp;
+          const int cnt = min(per_warp, total - e0);
+          int mine = -1;
+          if (lane < cnt) {
+            const int e = e0 + lane;
+            int lo = 0, hi = A.nchunks;  // invariant: off[lo] <= e < off[hi]
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (sm.l.off[mid] <= e) lo = mid; else hi = mid;
+            }
+            mine = __ldcg(A.left_list + (size_t)lo * FZ_THREADS + (e - sm.l.off[lo]));
+          }
+          float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
+          if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
+          Top5 t;
+          t.init(A.g.gate_d2);
+          int my_ext = 0;
+          for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
+            float4 q;
+            q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j);
+            q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
+            Top5 tj;
+            const int n_ext = warp_knn5(q, A.g, ge2, A.map_sorted, A.cell_start, lane, tj);
+            if (lane == j) { t = tj; my_ext = n_ext; }
+          }
+          if (mine >= 0) {
+            const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641
+            float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 nbr[5];
+            if (found) {
+              nbr[0] = __ldg(A.map4 + t.i(t.k0)); nbr[1] = __ldg(A.map4 + t.i(t.k1)); nbr[2] = __ldg(A.map4 + t.i(t.k2));
+              nbr[3] = __ldg(A.map4 + t.i(t.k3)); nbr[4] = __ldg(A.map4 + t.i(t.k4));
+              flag = plane_residual(ori, sel, nbr, coeff);
+              tie = t.tie();
+              if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (flag) jacobian_row(sTrig, ori, coeff, row, rhs);
+            fz_store_leftover(A, mine, sel, t, my_ext, ge2, found);
+            if (A.dbg.nn_idx) {
+              int* o = A.dbg.nn_idx + (size_t)mine * 5;
+              o[0] = found ? t.i(t.k0) : -1; o[1] = found ? t.i(t.k1) : -1; o[2] = found ? t.i(t.k2) : -1;
+              o[3] = found ? t.i(t.k3) : -1; o[4] = found ? t.i(t.k4) : -1;
+            }
+            if (A.dbg.nn_d2) {
+              float* o = A.dbg.nn_d2 + (size_t)mine * 5;
+              o[0] = t.d(t.k0); o[1] = t.d(t.k1); o[2] = t.d(t.k2); o[3] = t.d(t.k3); o[4] = t.d(t.k4);
+            }
+            if (A.dbg.coeff) A.dbg.coeff[mine] = coeff;
+            if (A.dbg.flag) A.dbg.flag[mine] = flag ? 1 : 0;
+            if (A.dbg.tie) A.dbg.tie[mine] = tie ? 1 : 0;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sm.l.rows[tid][k] = row[k];
+        sm.l.rows[tid][6] = rhs;
+        sm.l.rows[tid][7] = flag ? 1.f : 0.f;
+        if (flag && tie) ++ties;
+        __syncwarp();
+        if (ra.live) {  // every warp owns the slice of rows its own lanes staged
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float* rr = sm.l.rows[warp * 32 + r];
+            acc += (double)rr[ra.a] * (double)rr[ra.b];
+          }
+        }
+        __syncwarp();
+      }
+      {
+        int wt = ties;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
+        if (lane == 28) acc += (double)wt;
+      }
+      red[warp][lane] = acc;
       __syncthreads();
       if (tid < S2M_SUMS) {
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < FZ_WARPS; ++k) sum += red[k][tid];
-        red[0][tid] = sum;
+        if (tid == 31 && blockIdx.x == 0) sum += (double)total;
+        A.cta_rows[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
       }
+      if (probe && blockIdx.x == 0 && tid == 0) probe[4] = fz_globaltimer();
+      // ---- ticket B: the last CTA adds everything in a fixed order and runs the 6x6 tail ----
+      __threadfence();
       __syncthreads();
-      if (tid < 32) {
-        if (tid < 12) st->T_prev[tid] = sT[tid];  // where the points stood in this iteration
-        if (tid == 0) { st->certified = (int)red[0][30]; st->leftovers = total; }
-        __syncwarp();
-        lm_finalize_warp(st, red[0], s_fin, tid);
-        __syncwarp();
-        if (tid == 0) {
-          __threadfence();
-          atomicExch(&st->fz_release, (unsigned)(it + 1));
+      if (tid == 0) s_last = (atomicAdd(&st->fz_ticket_b[it], 1u) == (unsigned)(G - 1));
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (probe && tid == 0) probe[5] = fz_globaltimer();
+        const double sum_a = fz_reduce_rows(A.chunk_rows, A.nchunks, red, warp, lane);
+        const double sum_b = fz_reduce_rows(A.cta_rows, G, red, warp, lane);
+        if (tid < S2M_SUMS) s_sum[tid] = sum_a + sum_b;
+        if (probe && tid == 0) probe[6] = fz_globaltimer();
+        __syncthreads();
+        if (tid < 32) {
+          if (tid < 12) st->T_prev[tid] = sT[tid];
+          if (tid == 0) {
+            st->certified = (int)s_sum[30]; st->leftovers = (int)s_sum[31];
+            st->cert_hist[it] = (int)s_sum[30]; st->left_hist[it] = (int)s_sum[31]; st->seed_hist[it] = (int)s_sum[29];
+          }
+          __syncwarp();
+          lm_finalize_warp(st, s_sum, s_fin, tid);
+          __syncwarp();
+          if (tid == 0) {
+            if (probe) probe[7] = fz_globaltimer();
+            __threadfence();
+            atomicExch(&st->fz_phase, (unsigned)(2 * it + 2));
+          }
         }
       }
+      if (tid == 0) {
+        while (fz_ld_acquire(&st->fz_phase) < (unsigned)(2 * it + 2)) { }
+        __threadfence();
+      }
+      __syncthreads();
     }
-    // second barrier: wait for the tail
-    if (tid == 0) {
-      while (fz_ld_acquire(&st->fz_release) < (unsigned)(it + 1)) { }
-      __threadfence();
-      s_misc[1] = __ldcg(&st->done);
-    }
+    if (tid == 0) s_misc[1] = __ldcg(&st->done);
     __syncthreads();
-    if (A.probe && blockIdx.x == 0 && tid == 0) A.probe[it * 4 + 3] = fz_globaltimer();
     if (s_misc[1]) break;
   }
 }

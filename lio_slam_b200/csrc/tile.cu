@@ -189,14 +189,16 @@ int voxel_tile_dev(Ctx* c, const float4* pts, int n, float leaf, int tile, int n
     *n_out = m;
     *overflow = true;
     if (info) info->n_tile_points = m;
+    if (c->ev_mid) LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev_mid, c->stream));
     return LIOGPU_OK;
   }
   const int m = (int)plan.n_tile;
-  if (m <= 0) return LIOGPU_OK;
+  if (m <= 0) { if (c->ev_mid) LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev_mid, c->stream)); return LIOGPU_OK; }
   LIOGPU_CUDA_OK(c, c->tile_pts.reserve((size_t)m * sizeof(float4)));
   tile_compact_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(pts, n, d_plan, flag, c->tile_pts.as<float4>());
   c->launches++;
   LIOGPU_CUDA_OK(c, cudaGetLastError());
+  if (c->ev_mid) LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev_mid, c->stream));
   bool ov = false;
   return voxel_downsample_dev(c, c->tile_pts.as<float4>(), m, leaf, out, n_out, &ov);
 }

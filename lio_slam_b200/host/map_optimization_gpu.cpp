@@ -18,6 +18,12 @@ int ImageProjection::projectPointCloud() {
   return st;
 }
 
+int ImageProjection::projectPointCloudResident(const PointXYZIRT* raw, int n, int* n_out) {
+  const int enabled = (deskewFlag != -1 && imuAvailable) ? 1 : 0;  // imageProjection.cpp:547
+  return liogpu_deskew(ctx_, raw, n, sizeof(PointXYZIRT), timeScanCur, imuTime.data(), imuRotX.data(), imuRotY.data(),
+                       imuRotZ.data(), imuPointerCur + 1, enabled, LIOGPU_DEVICE_RESIDENT, sizeof(PointType), 0, n_out);
+}
+
 mapOptimization::mapOptimization(const liogpu_params& params) : params_(params) {
   const int st = liogpu_create(&ctx_, &params_);  // allocateMemory (mapOptmization.cpp:316-349)
   if (st != LIOGPU_OK) throw std::runtime_error("liogpu_create failed (no sm_100 GPU? there is no CPU fallback)");
@@ -163,6 +169,35 @@ void mapOptimization::downsampleAndScan2Map() {
   isDegenerate = deg != 0;
   laserCloudSurfLastDS.resize(lastStatus < 0 ? 0 : n_ds);
   laserCloudSurfLastDSNum = n_ds;
+}
+
+void mapOptimization::downsampleAndScan2MapResident() {
+  int n_ds = 0;
+  if (cloudKeyPoses3D.empty()) {  // scan2MapOptimization returns at once (:1841); downsampleCurrentScan still runs
+    lastStatus = liogpu_voxel_downsample(ctx_, LIOGPU_DEVICE_RESIDENT, 0, 16, params_.mapping_surf_leaf_size,
+                                         LIOGPU_DEVICE_RESIDENT, 16, 0, &n_ds);
+    laserCloudSurfLastDSNum = lastStatus < 0 ? 0 : n_ds;
+    return;
+  }
+  int deg = isDegenerate ? 1 : 0;
+  lastStatus = liogpu_downsample_scan2map(ctx_, LIOGPU_DEVICE_RESIDENT, 0, 16, transformTobeMapped, matP, &deg,
+                                          LIOGPU_MAX_ITER, &lastInfo, &n_ds, LIOGPU_DEVICE_RESIDENT, 16, 0);
+  isDegenerate = deg != 0;
+  laserCloudSurfLastDSNum = n_ds;
+}
+
+void mapOptimization::saveKeyFrameResident() {  // :2128-2142 without the factor graph
+  PointType p3{};
+  p3.x = transformTobeMapped[3]; p3.y = transformTobeMapped[4]; p3.z = transformTobeMapped[5];
+  p3.data3 = 1.0f;
+  p3.intensity = (float)cloudKeyPoses3D.size();
+  PointTypePose p6{};
+  p6.x = p3.x; p6.y = p3.y; p6.z = p3.z; p6.intensity = p3.intensity;
+  p6.roll = transformTobeMapped[0]; p6.pitch = transformTobeMapped[1]; p6.yaw = transformTobeMapped[2];
+  p6.time = timeLaserInfoCur;
+  lastStatus = liogpu_keyframe_put(ctx_, (int)cloudKeyPoses3D.size(), LIOGPU_DEVICE_RESIDENT, 0, 16);
+  cloudKeyPoses3D.push_back(p3);
+  cloudKeyPoses6D.push_back(p6);
 }
 
 Cloud mapOptimization::transformPointCloud(const Cloud& in, const PointTypePose& p) {

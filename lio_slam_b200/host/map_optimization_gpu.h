@@ -51,6 +51,9 @@ class ImageProjection {
   Cloud fullCloud;
   // imageProjection.cpp:577-615 (+ deskewPoint, findRotation) -> liogpu_deskew
   int projectPointCloud();
+  // the same call with the device-resident hand-off: the deskewed cloud stays in HBM for a
+  // co-located mapOptimization (same context); `raw` = laserCloudIn->points.data(), nothing is copied on the host
+  int projectPointCloudResident(const PointXYZIRT* raw, int n, int* n_out);
 
  private:
   liogpu_ctx* ctx_;
@@ -99,6 +102,10 @@ class mapOptimization {
   void downsampleCurrentScan();                          // :1605-1611 -> liogpu_voxel_downsample
   void scan2MapOptimization();                           // :1839-1865 -> liogpu_scan2map
   void downsampleAndScan2Map();                          // both fused on device -> liogpu_downsample_scan2map
+  // device-resident variants: the sweep is the context's resident cloud (left there by
+  // ImageProjection::projectPointCloudResident); laserCloudSurfLastDS stays in HBM, only its size comes back
+  void downsampleAndScan2MapResident();
+  void saveKeyFrameResident();                           // saveKeyFrame with thisSurfKeyFrame taken from the resident cloud
   Cloud transformPointCloud(const Cloud& in, const PointTypePose& pose);  // :849-868 -> liogpu_transform_cloud
   bool saveFrame() const;                                // :1909-1928 (host)
   void saveKeyFrame();                                   // the cloud/pose bookkeeping of saveKeyFramesAndFactor (:2128-2142)

@@ -40,7 +40,10 @@ class S2MInfo(C.Structure):
                 ("pose_hist", (C.c_float * 6) * LIOGPU_MAX_ITER), ("nsel_hist", C.c_int * LIOGPU_MAX_ITER),
                 ("gpu_ms", C.c_float), ("seeded", C.c_int), ("main_kernel_ms", C.c_float),
                 ("left_kernel_ms", C.c_float), ("main_kernel_launches", C.c_int), ("left_kernel_launches", C.c_int),
-                ("certified", C.c_int), ("leftovers", C.c_int), ("tail_ms", C.c_float), ("kernel_launches", C.c_int)]
+                ("certified", C.c_int), ("leftovers", C.c_int), ("tail_ms", C.c_float), ("kernel_launches", C.c_int),
+                ("certified_hist", C.c_int * LIOGPU_MAX_ITER), ("seeded_hist", C.c_int * LIOGPU_MAX_ITER),
+                ("leftover_hist", C.c_int * LIOGPU_MAX_ITER), ("main_us_hist", C.c_float * LIOGPU_MAX_ITER),
+                ("rest_us_hist", C.c_float * LIOGPU_MAX_ITER)]
 
 
 class LocalMapParams(C.Structure):
@@ -69,13 +72,19 @@ class IcpInfo(C.Structure):
                 ("gpu_ms", C.c_float), ("reserved", C.c_int * 5)]
 
 
+class TileInfo(C.Structure):
+    _fields_ = [("n_points", C.c_int), ("n_rows", C.c_int), ("n_bins", C.c_int), ("bin_lo", C.c_int), ("bin_hi", C.c_int),
+                ("n_tile_points", C.c_int), ("leaf_overflow", C.c_int), ("gpu_ms", C.c_float), ("plan_ms", C.c_float),
+                ("reserved", C.c_int * 3)]
+
+
 EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liogpu_destroy", "liogpu_last_error",
            "liogpu_host_alloc", "liogpu_host_free", "liogpu_deskew", "liogpu_transform_cloud",
            "liogpu_voxel_downsample", "liogpu_keyframe_put", "liogpu_keyframe_clear", "liogpu_keyframe_count",
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
            "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext", "liogpu_extract_nearby",
-           "liogpu_scan2map_trace"]
+           "liogpu_scan2map_trace", "liogpu_voxel_tile"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
 
@@ -120,6 +129,8 @@ def load_library() -> C.CDLL:
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_merge_keyframes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                            C.c_int, C.POINTER(C.c_int)]
+    lib.liogpu_voxel_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(TileInfo)]
     lib.liogpu_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
     lib.liogpu_extract_nearby.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
@@ -196,7 +207,9 @@ def info_to_dict(info: S2MInfo) -> dict:
                 main_kernel_ms=info.main_kernel_ms, left_kernel_ms=info.left_kernel_ms,
                 main_kernel_launches=info.main_kernel_launches, left_kernel_launches=info.left_kernel_launches,
                 certified=info.certified, leftovers=info.leftovers, tail_ms=info.tail_ms,
-                kernel_launches=info.kernel_launches)
+                kernel_launches=info.kernel_launches, certified_hist=np.array(info.certified_hist)[:it],
+                seeded_hist=np.array(info.seeded_hist)[:it], leftover_hist=np.array(info.leftover_hist)[:it],
+                main_us_hist=np.array(info.main_us_hist)[:it], rest_us_hist=np.array(info.rest_us_hist)[:it])
 
 
 class LioGpu:
@@ -304,6 +317,30 @@ class LioGpu:
         st = self._check(self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
                                                          C.c_float(leaf), C.byref(n_map), None, 16, 0))
         return n_map.value, st
+
+    def voxel_tile(self, ids, poses, leaf: float, tile: int, n_tiles: int, out=None):
+        """Tile `tile` of `n_tiles` of extractCloud's VoxelGrid (liogpu_voxel_tile).  out: None -> host array returned;
+        (device_ptr, capacity) -> written there (packed float4), only the count returned.  -> (cloud | n, info, status)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6)
+        info = TileInfo()
+        n_out = C.c_int(0)
+        if out is None:
+            st = self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf), tile,
+                                            n_tiles, None, 16, 0, C.byref(n_out), C.byref(info))
+            self._check(st)
+            host = np.empty((max(n_out.value, 1), 4), np.float32)
+            st = self._check(self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf),
+                                                        tile, n_tiles, host.ctypes.data, 16, host.shape[0], C.byref(n_out),
+                                                        C.byref(info)))
+            res = host[: n_out.value].copy()
+        else:
+            ptr, cap = out
+            st = self._check(self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf),
+                                                        tile, n_tiles, int(ptr), 16, int(cap), C.byref(n_out), C.byref(info)))
+            res = n_out.value
+        d = {k: getattr(info, k) for k, _ in TileInfo._fields_ if k != "reserved"}
+        return res, d, st
 
     def publish_local_map(self, ids, poses, pose_now, params: "LocalMapParams | None" = None, **over):
         """publishLocalMap (mapOptmization.cpp:2442-2541) -> (cloud (n,4), info dict, status)."""

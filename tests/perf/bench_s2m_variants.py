@@ -50,6 +50,12 @@ def main():
                     ms.append(info["gpu_ms"]); iters.append(info["iterations"])
                     main += info["main_kernel_ms"]; left += info["left_kernel_ms"]; tail += info["tail_ms"]
                     cert.append(info["certified"]); lo.append(info["leftovers"])
+                    if prof == 1 and s == 3:
+                        res["one_registration"] = dict(
+                            main_us=[round(float(x), 1) for x in info["main_us_hist"]],
+                            rest_us=[round(float(x), 1) for x in info["rest_us_hist"]],
+                            seeded=info["seeded_hist"].tolist(), certified=info["certified_hist"].tolist(),
+                            leftovers=info["leftover_hist"].tolist(), nsel=info["nsel_hist"].tolist())
                     if s < 3 + len(scans):
                         hist.append((info["iterations"], info["nsel_hist"].tolist(), pose.tolist()))
                 g.close()
@@ -65,7 +71,7 @@ def main():
                 ref_hist = hist
             same = all(a[0] == b[0] and a[1] == b[1] for a, b in zip(hist, ref_hist))
             pose_eq = all(a[2] == b[2] for a, b in zip(hist, ref_hist))
-            print(json.dumps(dict(workload=name, variant=var, n_query=int(scans[0].shape[0]), same_iterations_and_nsel=same,
+            print(json.dumps(dict(workload=name, variant=var, lib=os.environ.get("LIOGPU_LIB", "default"), n_query=int(scans[0].shape[0]), same_iterations_and_nsel=same,
                                   poses_bit_equal_to_first_variant=pose_eq, **res)), flush=True)
             assert same, "variants disagree on iteration counts / nsel history"
 

@@ -39,8 +39,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(liogpu.Params) == 4 * 21
     # liogpu_s2m_info: 6 int + 2 float + 36 + 6 double + 30*6 float + 30 int + float (+ padding to 8)
     # ... + gpu_ms, seeded, 2 float kernel times, 2 int launch counts (6 x 4 bytes)
-    # ... + certified, leftovers, tail_ms, kernel_launches (4 x 4 bytes)
-    assert C.sizeof(liogpu.S2MInfo) == 8 * 4 + 42 * 8 + 180 * 4 + 30 * 4 + 6 * 4 + 4 * 4
+    # ... + certified, leftovers, tail_ms, kernel_launches (4 x 4 bytes) + five per-iteration histories
+    assert C.sizeof(liogpu.S2MInfo) == 8 * 4 + 42 * 8 + 180 * 4 + 30 * 4 + 6 * 4 + 4 * 4 + 5 * 30 * 4
 
 
 def test_struct_layouts_match_a_c_compiler(tmp_path):

@@ -346,6 +346,55 @@ def test_tiled_voxel_rebuild_on_gpu(gpu, oracle, world, tiles):
     assert_biteq(got, want, f"{tiles} tiles")
 
 
+@pytest.mark.parametrize("tiles", [1, 2, 3, 4, 8])
+def test_device_planned_tiles_equal_build_local_map(gpu, oracle, world, tiles):
+    # liogpu_voxel_tile: the tile plan (coarse histogram of the voxel-row index) is made on the device; the tiles'
+    # outputs concatenated in tile order must equal extractCloud's single-GPU output and the oracle's, bit for bit
+    clouds, poses = [], []
+    for k in range(8):
+        p = synth.path_pose(-0.8 * k)
+        clouds.append(synth.to_packed(synth.make_scan(world, p, 32, seed=500 + k, cols=600)))
+        poses.append(p.astype(np.float32))
+    poses = np.array(poses)
+    want, ov = oracle.build_local_map(clouds, poses, 0.5, threads=8)
+    assert not ov
+    gpu.keyframe_clear()
+    for k, c in enumerate(clouds):
+        gpu.keyframe_put(k, c)
+    ids = np.arange(8)
+    single, st = gpu.build_local_map(ids, poses, 0.5, fetch=True, cap=want.shape[0])
+    assert_biteq(single, want, "single GPU")
+    parts, npts = [], 0
+    for t in range(tiles):
+        out, info, st = gpu.voxel_tile(ids, poses, 0.5, t, tiles)
+        assert st == 0 and info["n_points"] == sum(c.shape[0] for c in clouds)
+        npts += info["n_tile_points"]
+        parts.append(out)
+    assert npts == sum(c.shape[0] for c in clouds)                    # every point belongs to exactly one tile
+    sizes = [p.shape[0] for p in parts]
+    assert_biteq(np.concatenate(parts), want, f"{tiles} device-planned tiles")
+    if tiles > 1:
+        assert max(sizes) < 0.8 * want.shape[0]                       # the plan actually splits the work
+    # the installed local map of the registration is untouched by the tile calls
+    assert gpu.local_map_size() == want.shape[0]
+    print(f"tiles={tiles} voxels per tile={sizes}")
+
+
+def test_device_planned_tiles_overflow_guard(gpu, oracle, small_case):
+    # leaf 0.01 over a 100 m sweep: the guard of the WHOLE cloud fires (q4) -> the concatenated tiles are the input
+    gpu.keyframe_clear()
+    gpu.keyframe_put(0, small_case["scan4"])
+    pose = np.zeros((1, 6), np.float32)
+    want, ov = oracle.build_local_map([small_case["scan4"]], pose, 0.01, threads=2)
+    assert ov
+    parts = []
+    for t in range(3):
+        out, info, st = gpu.voxel_tile([0], pose, 0.01, t, 3)
+        assert st == 1 and info["leaf_overflow"] == 1
+        parts.append(out)
+    assert_biteq(np.concatenate(parts), want, "overflow guard")
+
+
 def test_scan2map_full_size_properties(gpu):
     # BASELINE-size property checks that need no oracle run: a 64-beam sweep registered against a map built
     # from the same world converges toward ground truth from different perturbations, and re-running is
