@@ -55,6 +55,10 @@ typedef struct liogpu_ctx liogpu_ctx;
  * LIOGPU_DEVICE_RESIDENT input then fails with LIOGPU_E_INVALID rather than reading other data). */
 #define LIOGPU_DEVICE_RESIDENT ((void*)(unsigned long long)1)
 
+/* As an INPUT cloud pointer of liogpu_scan2map, liogpu_downsample_scan2map, liogpu_voxel_downsample or
+ * liogpu_keyframe_put (n and stride are then ignored): the sweep a preceding liogpu_upload_scan_async put on its way. */
+#define LIOGPU_UPLOADED_SCAN ((void*)(unsigned long long)2)
+
 /* Parameters the hot path reads from ParamServer (UT:199-331); defaults are UT's compiled-in ones.
  * Fill with liogpu_default_params() and override. */
 typedef struct liogpu_params {
@@ -336,6 +340,19 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
 int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6],
                           float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info,
                           int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag, unsigned char* tie);
+
+/* Start copying a sweep to the GPU on the context's copy stream and return at once.  The node calls it when the message
+ * arrives (pcl::fromROSMsg, MO:440), BEFORE it takes `mtx` (MO:449): the copy then overlaps the registration of the
+ * previous sweep, and the next call that names LIOGPU_UPLOADED_SCAN as its input waits for it on the device.  The
+ * caller's buffer must stay valid until that call returns (pinned memory — liogpu_host_alloc — for a truly
+ * asynchronous copy).  Two sweeps may be in flight.  Unlike every other entry point it may overlap ONE other call
+ * on the same context. */
+int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int stride);
+
+/* Copy out the cloud produced by the call RIGHT BEFORE this one (liogpu_build_local_map, liogpu_merge_keyframes,
+ * liogpu_publish_local_map, liogpu_voxel_tile) without recomputing it: a caller that does not know the size passes
+ * cap_out = 0 to the producing call, reads the size from its LIOGPU_E_CAPACITY return, sizes its buffer and fetches. */
+int liogpu_fetch_result(liogpu_ctx* ctx, void* xyzi_out, int out_stride, int cap_out, int* n_out);
 
 /* Timing hook for bench.py: device milliseconds of the last call's kernels (events on ctx's stream). */
 float liogpu_last_gpu_ms(const liogpu_ctx* ctx);

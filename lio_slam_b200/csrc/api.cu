@@ -7,6 +7,8 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler is attached
+
 using namespace liogpu;
 
 struct liogpu_ctx {
@@ -16,6 +18,12 @@ struct liogpu_ctx {
 namespace {
 
 thread_local std::string g_create_err;
+
+// one NVTX range per ABI entry point (the reference's commented-out per-stage timers, MO:461-501)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -36,6 +44,22 @@ int load_cloud(Ctx* c, const void* src, int& n, int stride, DevBuf& dst) {
     if (c->resident == &dst || n == 0) return LIOGPU_OK;
     LIOGPU_CUDA_OK(c, dst.reserve((size_t)n * sizeof(float4)));
     LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst.p, c->resident->p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    return LIOGPU_OK;
+  }
+  if (src == LIOGPU_UPLOADED_SCAN) {  // the sweep liogpu_upload_scan_async put on its way
+    if (c->upload_ready < 0 || !c->upload[c->upload_ready].valid) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    Ctx::Upload& u = c->upload[c->upload_ready];
+    u.valid = false;
+    c->upload_ready = -1;
+    n = u.n;
+    LIOGPU_CUDA_OK(c, dst.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4)));
+    if (n == 0) return LIOGPU_OK;
+    LIOGPU_CUDA_OK(c, cudaStreamWaitEvent(c->stream, u.ev, 0));
+    if (u.stride == 16) {
+      LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dst.p, u.raw.p, (size_t)n * 16, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      LIOGPU_CUDA_OK(c, launch_unpack(c, u.raw.p, n, u.stride, dst.as<float4>()));
+    }
     return LIOGPU_OK;
   }
   if (n < 0 || (n > 0 && !src) || !stride_ok(stride)) { c->err = "bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
@@ -98,15 +122,24 @@ int stage_keyframes(Ctx* c, const char* who, const int* ids, const float* pose6s
     t.total += (size_t)it->second.second;
   }
   if (t.total > 0x7fffffffULL) { c->err = std::string(who) + ": cloud too large"; return LIOGPU_E_INVALID; }
-  if ((size_t)k * 6 * sizeof(float) > 32768) {
-    c->err = std::string(who) + ": too many keyframes in one call (max 1365)";
-    return LIOGPU_E_INVALID;
-  }
   if (t.total == 0) return LIOGPU_OK;
-  char* hp = (char*)c->h_pinned + 131072;
+  // tables sized from k (saveMapService merges EVERY keyframe of a run, mapOptmization.cpp:936-941): poses | offsets | pointers
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t off_offs = up256((size_t)k * 6 * sizeof(float));
+  const size_t off_srcs = off_offs + up256(((size_t)k + 1) * sizeof(int));
+  const size_t tab_bytes = off_srcs + up256((size_t)k * sizeof(void*));
+  if (tab_bytes > c->h_kf_cap) {  // nothing of this context is in flight here: every call ends with a stream sync
+    if (c->h_kf_tab) cudaFreeHost(c->h_kf_tab);
+    c->h_kf_tab = nullptr;
+    c->h_kf_cap = 0;
+    const size_t want = tab_bytes + tab_bytes / 2 + 4096;
+    LIOGPU_CUDA_OK(c, cudaHostAlloc(&c->h_kf_tab, want, cudaHostAllocDefault));
+    c->h_kf_cap = want;
+  }
+  char* hp = (char*)c->h_kf_tab;
   float* hposes = reinterpret_cast<float*>(hp);
-  int* hoffs = reinterpret_cast<int*>(hp + 32768);
-  const float4** hsrcs = reinterpret_cast<const float4**>(hp + 49152);
+  int* hoffs = reinterpret_cast<int*>(hp + off_offs);
+  const float4** hsrcs = reinterpret_cast<const float4**>(hp + off_srcs);
   std::memcpy(hposes, pose6s, (size_t)k * 6 * sizeof(float));
   size_t off = 0;
   for (int f = 0; f < k; ++f) {
@@ -116,19 +149,20 @@ int stage_keyframes(Ctx* c, const char* who, const int* ids, const float* pose6s
     off += (size_t)kf.second;
   }
   hoffs[k] = (int)off;
-  LIOGPU_CUDA_OK(c, c->dbg_d2.reserve(65536 + (size_t)k * 12 * sizeof(float)));  // scratch: tables + k transforms
-  char* dp = (char*)c->dbg_d2.p;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, 65536, cudaMemcpyHostToDevice, c->stream));
-  t.srcs = reinterpret_cast<const float4* const*>(dp + 49152);
-  t.offs = reinterpret_cast<const int*>(dp + 32768);
+  LIOGPU_CUDA_OK(c, c->kf_tab.reserve(tab_bytes + (size_t)k * 12 * sizeof(float)));  // tables + k transforms
+  char* dp = (char*)c->kf_tab.p;
+  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(dp, hp, tab_bytes, cudaMemcpyHostToDevice, c->stream));
+  t.srcs = reinterpret_cast<const float4* const*>(dp + off_srcs);
+  t.offs = reinterpret_cast<const int*>(dp + off_offs);
   t.poses = reinterpret_cast<const float*>(dp);
-  t.T12 = reinterpret_cast<float*>(dp + 65536);
+  t.T12 = reinterpret_cast<float*>(dp + tab_bytes);
   return LIOGPU_OK;
 }
 
 int enter(liogpu_ctx* ctx) {
   if (!ctx) return LIOGPU_E_INVALID;
   ctx->c.err.clear();
+  ctx->c.last_result = nullptr;  // liogpu_fetch_result serves only the call right before it
   if (cudaSetDevice(ctx->c.device) != cudaSuccess) {
     ctx->c.err = std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError());
     return LIOGPU_E_CUDA;
@@ -187,6 +221,9 @@ int liogpu_create(liogpu_ctx** out, const liogpu_params* params) {
       cudaEventCreateWithFlags(&c.ev_it0, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c.ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c.ev0) != cudaSuccess || cudaEventCreate(&c.ev1) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.upload[0].ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c.upload[1].ev, cudaEventDisableTiming) != cudaSuccess ||
       cudaHostAlloc(&c.h_pinned, 262144, cudaHostAllocDefault) != cudaSuccess) {
     liogpu_destroy(ctx);
     return LIOGPU_E_CUDA;
@@ -205,6 +242,11 @@ void liogpu_destroy(liogpu_ctx* ctx) {
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
   if (c.side_stream) cudaStreamSynchronize(c.side_stream);
+  if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
+  for (auto& u : c.upload) { u.raw.release(); if (u.ev) cudaEventDestroy(u.ev); }
+  if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+  if (c.h_kf_tab) cudaFreeHost(c.h_kf_tab);
+  c.kf_tab.release();
   DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
                     &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
                     &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
@@ -242,6 +284,7 @@ void liogpu_host_free(void* p) {
 int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double time_scan_cur, const double* imu_time,
                   const double* imu_rot_x, const double* imu_rot_y, const double* imu_rot_z, int n_imu,
                   int deskew_enabled, void* xyzi_out, int out_stride, int cap_out, int* n_out) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -287,6 +330,7 @@ int liogpu_deskew(liogpu_ctx* ctx, const void* xyzirt, int n, int stride, double
 
 int liogpu_transform_cloud(liogpu_ctx* ctx, const void* xyzi, int n, int stride, const float pose6[6], void* xyzi_out,
                            int out_stride) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -313,6 +357,7 @@ int liogpu_transform_cloud(liogpu_ctx* ctx, const void* xyzi, int n, int stride,
 
 int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride, float leaf, void* xyzi_out,
                             int out_stride, int cap_out, int* n_out) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -344,18 +389,30 @@ int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride
 }
 
 int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int stride) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
+  // arguments are checked BEFORE the table is touched, and the cloud is loaded into a buffer of its own that replaces
+  // the old one only on success: a failed overwrite keeps the previous keyframe and nothing leaks
+  const bool special = xyzi == LIOGPU_DEVICE_RESIDENT || xyzi == LIOGPU_UPLOADED_SCAN;
+  if (!special && (n < 0 || (n > 0 && !xyzi) || !stride_ok(stride))) { c->err = "liogpu_keyframe_put: bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
+  DevBuf fresh;
+  rc = load_cloud(c, xyzi, n, stride, fresh);
+  if (rc == LIOGPU_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {  // raw_in staging is reused by the next call
+    c->err = std::string("liogpu_keyframe_put: ") + cudaGetErrorString(cudaGetLastError());
+    rc = LIOGPU_E_CUDA;
+  }
+  if (rc) { fresh.release(); return rc; }
   auto& slot = c->keyframes[id];
-  rc = load_cloud(c, xyzi, n, stride, slot.first);
-  if (rc) { c->keyframes.erase(id); return rc; }
+  slot.first.release();
+  slot.first = fresh;
   slot.second = n;
-  LIOGPU_CUDA_OK(c, cudaStreamSynchronize(c->stream));  // raw_in staging is reused by the next call
   return LIOGPU_OK;
 }
 
 int liogpu_keyframe_clear(liogpu_ctx* ctx) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -369,6 +426,7 @@ int liogpu_keyframe_count(const liogpu_ctx* ctx) { return ctx ? (int)ctx->c.keyf
 
 int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, int* n_map,
                            void* xyzi_out, int out_stride, int cap_out) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -393,6 +451,7 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_map = m;
+  c->last_result = c->map4.as<float4>(); c->last_result_n = m;
   if (xyzi_out) {
     if (m > cap_out) { c->err = "liogpu_build_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->map4.as<float4>(), m, xyzi_out, out_stride);
@@ -405,6 +464,7 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
 
 int liogpu_voxel_tile(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, int tile, int n_tiles,
                       void* xyzi_out, int out_stride, int cap_out, int* n_out, liogpu_tile_info* info) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -432,6 +492,7 @@ int liogpu_voxel_tile(liogpu_ctx* ctx, const int* ids, const float* pose6s, int 
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
+  c->last_result = c->tile_out.as<float4>(); c->last_result_n = m;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_voxel_tile: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->tile_out.as<float4>(), m, xyzi_out, out_stride);
@@ -461,6 +522,7 @@ void liogpu_default_local_map_params(liogpu_local_map_params* p) {
 int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, const float pose_now[6],
                              const liogpu_local_map_params* params, void* xyzi_out, int out_stride, int cap_out,
                              int* n_out, liogpu_local_map_info* info) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -513,6 +575,7 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
+  c->last_result = result; c->last_result_n = m;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_publish_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, result, m, xyzi_out, out_stride);
@@ -526,6 +589,7 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
 
 int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s, int k, float leaf, void* xyzi_out,
                            int out_stride, int cap_out, int* n_out) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -550,6 +614,7 @@ int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   }
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
+  c->last_result = result; c->last_result_n = m;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_merge_keyframes: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, result, m, xyzi_out, out_stride);
@@ -572,6 +637,7 @@ void liogpu_default_icp_params(liogpu_icp_params* p, float history_keyframe_sear
 int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int source_stride, const void* target_xyzi,
                      int n_target, int target_stride, const liogpu_icp_params* params, float final_transformation[16],
                      liogpu_icp_info* info) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -593,6 +659,7 @@ int liogpu_icp_align(liogpu_ctx* ctx, const void* source_xyzi, int n_source, int
 
 int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride, double lidar_height, double max_radius,
                             double* desc, double* ringkey, double* sectorkey) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -620,6 +687,7 @@ int liogpu_make_scancontext(liogpu_ctx* ctx, const void* xyzi, int n, int stride
 int liogpu_extract_nearby(liogpu_ctx* ctx, const void* key_poses3d, int n_key, int stride3d, const void* key_times,
                           int time_stride, double time_laser_info_cur, float search_radius, float density_leaf, int* ids_out,
                           int cap_ids, int* n_ids) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -639,6 +707,7 @@ int liogpu_extract_nearby(liogpu_ctx* ctx, const void* key_poses3d, int n_key, i
 }
 
 int liogpu_set_local_map(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -671,6 +740,7 @@ static int s2m_guards(Ctx* c, int n, liogpu_s2m_info* info) {
 
 int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6], float matP_io[36],
                     int* degenerate_io, int max_iter, liogpu_s2m_info* info) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -678,6 +748,10 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
   if (scan_ds == LIOGPU_DEVICE_RESIDENT) {
     if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
     n = c->resident_n;
+  }
+  if (scan_ds == LIOGPU_UPLOADED_SCAN) {
+    if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    n = c->upload[c->upload_ready].n;
   }
   rc = s2m_guards(c, n, info);
   if (rc) {
@@ -693,6 +767,7 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
 int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6], float matP_io[36],
                           int* degenerate_io, int max_iter, liogpu_s2m_info* info, int* nn_idx, float* nn_d2, float* coeff,
                           unsigned char* flag, unsigned char* tie) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -700,6 +775,10 @@ int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int strid
   if (scan_ds == LIOGPU_DEVICE_RESIDENT) {
     if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; }
     n = c->resident_n;
+  }
+  if (scan_ds == LIOGPU_UPLOADED_SCAN) {
+    if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    n = c->upload[c->upload_ready].n;
   }
   rc = s2m_guards(c, n, info);
   if (rc) {
@@ -716,6 +795,7 @@ int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int strid
 int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int stride, float pose_io[6],
                                float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info, int* n_ds,
                                void* scan_ds_out, int out_stride, int cap_out) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -751,6 +831,7 @@ int liogpu_downsample_scan2map(liogpu_ctx* ctx, const void* scan, int n, int str
 int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, const float* pose6,
                              const float* T12, int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag,
                              unsigned char* tie) {
+  NvtxRange nvtx_range_(__func__);
   int rc = enter(ctx);
   if (rc) return rc;
   Ctx* c = &ctx->c;
@@ -775,6 +856,39 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
   if (rc) return rc;
   if (scan_ds != LIOGPU_DEVICE_RESIDENT) clobber(c, &c->scan_ds4);
   return surf_optimization_dev(c, c->scan_ds4.as<float4>(), n, pose6, T12, nn_idx, nn_d2, coeff, flag, tie);
+}
+
+int liogpu_fetch_result(liogpu_ctx* ctx, void* xyzi_out, int out_stride, int cap_out, int* n_out) {
+  NvtxRange nvtx_range_(__func__);
+  if (!ctx) return LIOGPU_E_INVALID;
+  Ctx* c = &ctx->c;
+  c->err.clear();
+  if (cudaSetDevice(c->device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return LIOGPU_E_CUDA; }
+  if (!n_out) { c->err = "liogpu_fetch_result: null n_out"; return LIOGPU_E_INVALID; }
+  if (!c->last_result) { c->err = "liogpu_fetch_result: no result pending (it serves only the call right before it)"; return LIOGPU_E_INVALID; }
+  *n_out = c->last_result_n;
+  if (c->last_result_n > cap_out) { c->err = "liogpu_fetch_result: output capacity too small"; return LIOGPU_E_CAPACITY; }
+  return store_cloud(c, c->last_result, c->last_result_n, xyzi_out, out_stride);
+}
+
+int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {
+  NvtxRange nvtx_range_(__func__);
+  if (!ctx) return LIOGPU_E_INVALID;
+  Ctx* c = &ctx->c;
+  // touches only the upload slots and the copy stream, so it may overlap ONE other call on the context (the node
+  // starts the copy when the message arrives, before it takes mtx)
+  if (cudaSetDevice(c->device) != cudaSuccess) return LIOGPU_E_CUDA;
+  if (n < 0 || (n > 0 && !xyzi) || !stride_ok(stride)) return LIOGPU_E_INVALID;
+  Ctx::Upload& u = c->upload[c->upload_next];
+  if (u.raw.reserve((size_t)(n > 0 ? n : 1) * stride) != cudaSuccess) return LIOGPU_E_CUDA;
+  if (n > 0 && cudaMemcpyAsync(u.raw.p, xyzi, (size_t)n * stride,
+                               is_device_ptr(xyzi) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess)
+    return LIOGPU_E_CUDA;
+  if (cudaEventRecord(u.ev, c->copy_stream) != cudaSuccess) return LIOGPU_E_CUDA;
+  u.n = n; u.stride = stride; u.valid = true;
+  c->upload_ready = c->upload_next;
+  c->upload_next ^= 1;
+  return LIOGPU_OK;
 }
 
 float liogpu_last_gpu_ms(const liogpu_ctx* ctx) { return ctx ? ctx->c.last_ms : 0.f; }

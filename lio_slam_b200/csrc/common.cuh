@@ -145,6 +145,17 @@ struct Ctx {
   // device-resident hand-off (LIOGPU_DEVICE_RESIDENT)
   DevBuf* resident = nullptr;
   int resident_n = 0;
+  // keyframe tables of the multi-keyframe calls (poses | offsets | source pointers), sized from k
+  void* h_kf_tab = nullptr;
+  size_t h_kf_cap = 0;
+  DevBuf kf_tab;
+  // result of the last build_local_map / merge_keyframes / publish_local_map / voxel_tile, for liogpu_fetch_result
+  const float4* last_result = nullptr;
+  int last_result_n = 0;
+  // liogpu_upload_scan_async: two staging slots filled on a copy stream
+  cudaStream_t copy_stream = nullptr;
+  struct Upload { DevBuf raw; cudaEvent_t ev = nullptr; int n = 0, stride = 0; bool valid = false; } upload[2];
+  int upload_next = 0, upload_ready = -1;
 };
 
 #define LIOGPU_CUDA_OK(ctx, expr)                                                        \

@@ -27,6 +27,8 @@
 // Algorithmic HBM bytes per launch: 16 B query + 5 x 16 B neighbours = 96 B per sweep point.
 #include "common.cuh"
 #include "pose_math.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace liogpu {
 
@@ -234,12 +236,15 @@ __device__ __forceinline__ u64 warp_min_u64(const u64 v) {
 // gate_ext_d2 >= gate_d2: every map point closer than sqrt(gate_ext_d2) is visited and COUNTED (return value,
 // warp-uniform), while only points inside gate_d2 compete for the five slots.  The count feeds the
 // "hopeless point" rule of the main kernel (see HOPELESS_* below).
+// init_d2 (< 0: the gate): the sentinel of the lists, i.e. only points closer than sqrt(init_d2) compete for the five
+// slots; the fused loop passes the search radius itself to learn the 5th distance even when it lies beyond the gate.
 __device__ __forceinline__ int warp_knn5(const float4 q, const GridParams& g, const float gate_ext_d2,
                                          const float4* __restrict__ map_sorted,
-                                         const uint32_t* __restrict__ cell_start, const int lane, Top5& out) {
+                                         const uint32_t* __restrict__ cell_start, const int lane, Top5& out,
+                                         const float init_d2 = -1.f) {
   Top5 t;
-  t.init(g.gate_d2);
-  out.init(g.gate_d2);
+  t.init(init_d2 < 0.f ? g.gate_d2 : init_d2);
+  out.init(init_d2 < 0.f ? g.gate_d2 : init_d2);
   int n_ext = 0;
   const float s2 = 2.0f * g.slack;
   const float reach = sqrtf(gate_ext_d2) * 1.000001f + s2;
@@ -1334,6 +1339,14 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
       }
       info->main_kernel_ms = (float)(m * 1e-6); info->left_kernel_ms = (float)(l * 1e-6); info->tail_ms = (float)(t * 1e-6);
       info->main_kernel_launches = cnt; info->left_kernel_launches = cnt;
+      if (getenv("LIOGPU_PRINT_PROBES")) {  // development aid: every stamp relative to the iteration's start, us
+        for (int it = 0; it < cnt; ++it) {
+          const unsigned long long* p = h_probe + it * FZ_PROBES;
+          fprintf(stderr, "[liogpu probes] it %d:", it);
+          for (int k = 1; k < FZ_PROBES; ++k) fprintf(stderr, " p%d=%.1f", k, p[k] ? (double)(p[k] - p[0]) * 1e-3 : -1.0);
+          fprintf(stderr, "  cert=%d seeded=%d left=%d\n", h->cert_hist[it], h->seed_hist[it], h->left_hist[it]);
+        }
+      }
     }
   }
   if (h->cert_mismatch) { c->err = "internal: eigen certificate contradicted by the exact computation"; return LIOGPU_E_INVALID; }

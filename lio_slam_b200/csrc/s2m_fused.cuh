@@ -7,23 +7,27 @@
 //
 //   per Gauss-Newton iteration
 //     main phase   chunks of 256 sweep points pulled from an atomic queue (no wave tail: a CTA that finishes
-//                  early takes the next chunk).  Per chunk, three steps separated by __syncthreads:
-//                    1 classify  thread = point.  From iteration 1 on every point carries a CANDIDATE SET: the (up
+//                  early takes the next chunk).  Inside a chunk every WARP works on its 32 points on its own (no
+//                  block-wide step until the final reduction, so warps of a CTA overlap freely):
+//                    1 classify  lane = point.  From iteration 1 on every point carries a CANDIDATE SET: the (up
 //                                to) 8 nearest map points found by its last search and a lower bound `lb` on the
 //                                distance from the point to every map point outside the set.  The set members'
 //                                distances to the moved point are evaluated exactly; if the 5th smallest is
 //                                below lb - |move| (triangle inequality, rounding margins included) the five
 //                                nearest neighbours of the moved point are certainly inside the set: they are
 //                                selected and ordered by (d2, map index) with no grid walk at all — an exact
-//                                certificate, not a heuristic.  Otherwise the point is queued for a search.
-//                    2 search    the queued points, COMPACTED over the CTA (dense lanes), walk the sorted grid
-//                                for the 9 nearest inside the seeded bound (or the phase-1 gate): exact 5-NN +
-//                                the next candidate set + its bound.  Points phase 1 cannot settle go to the
-//                                chunk's segment of the leftover list.
-//                    3 fit       thread = point: 5x3 plane fit, weight, Jacobian row; FP64 block reduction of the
-//                                27 sums of A^T A / A^T b into the chunk's partial row.
-//                  A chunk with at most 8 such points finishes them on the spot (one warp-cooperative full-gate search
-//                  per warp); a chunk with more defers them to the grid-wide leftover phase.
+//                                certificate, not a heuristic.  Otherwise the point needs a search.
+//                    2 search    iteration 0 (no sets yet, and the first step is too large for a set to survive):
+//                                the 5-nearest walk of the sorted grid inside the phase-1 gate, lane = point.
+//                                Later iterations: the 9-nearest walk inside the seeded bound (exact 5-NN + the next
+//                                candidate set + its bound), lane = point when many lanes need it; when only a
+//                                few do (the usual case once the certificate bites) the warp serves them one by
+//                                one COOPERATIVELY (lanes share rows and candidates: ~2 us instead of a ~13 us
+//                                single-lane chain).
+//                    3 leftovers points phase 1 cannot settle: up to 4 per warp are finished on the spot by the
+//                                warp-cooperative full-gate search, more are deferred to the grid-wide phase.
+//                    4 fit       lane = point: 5x3 plane fit, weight, Jacobian row; FP64 reduction of the 27 sums
+//                                of A^T A / A^T b over the warp's rows, then over the chunk's warps.
 //     ticket A     the last CTA to finish the main phase looks at the number of deferred leftovers:
 //                    none (the usual case from iteration 1 on): it adds the chunk rows in a fixed order, runs the
 //                          6x6 tail of LMOptimization (lm_finalize_warp) and releases the others — ONE grid-wide
@@ -46,8 +50,8 @@ constexpr int FZ_K = LIOGPU_FZ_K;        // members of a candidate set
 constexpr int FZ_MAXCHUNKS = 4096;       // chunk-offset table of the leftover phase lives in shared memory
 constexpr float FZ_REL = 1e-5f;          // relative safety margin of every bound (f32 rounding is < 3e-7)
 constexpr float FZ_SEED_MARGIN = 0.10f;  // a seeded search enumerates this far (m) beyond the seeds' 5th distance
-constexpr int FZ_DIRECT_MIN = 128;       // chunks with more search requests than this skip the compaction (thread = point)
-constexpr int FZ_INPLACE = FZ_WARPS;     // chunks with at most this many leftovers finish them on the spot
+constexpr int FZ_WCOOP_MAX = 4;          // a warp with at most this many search requests serves them cooperatively, one by one
+constexpr int FZ_INPLACE = 4;            // a warp with at most this many leftovers finishes them on the spot
 constexpr int FZ_PROBES = 8;             // %globaltimer stamps per iteration (profile_kernels)
 
 // ---- 9 best (d2, map index) pairs, same 64-bit keys as Top5; slot FZ_K is the pruning threshold ----
@@ -227,14 +231,96 @@ __device__ __forceinline__ void fz_matp_warp(LmDevState* st, FinSmem& m, const i
   }
 }
 
+// Warp-cooperative exact search of ONE query inside gate_d2 (all lanes pass the same q): the five nearest in
+// ascending (d2, index), up to FZ_K - 5 further candidates, lb2 = a lower bound on d2 of every map point that is not
+// returned, d6 = the best d2 among the points outside the five (tie logging).  Same row / candidate hand-out as
+// warp_knn5; every lane returns the same values.  Empty slots of `out` hold ~0.
+__device__ __forceinline__ void warp_knn_set(const float4 q, const GridParams& g, const float gate_d2,
+                                             const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start,
+                                             const int lane, u64 out[FZ_K], float& lb2, float& d6) {
+  Top5 t;
+  t.init(gate_d2);
+  const float s2 = 2.0f * g.slack;
+  const float reach = sqrtf(gate_d2) * 1.000001f + s2;
+  int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
+  int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
+  zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
+  ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
+  const int nys = ymax - ymin + 1;
+  const int nrows = (zmin > zmax || ymin > ymax) ? 0 : (zmax - zmin + 1) * nys;
+  for (int base = 0; base < nrows; base += 32) {
+    const int r = base + lane;
+    uint32_t s = 0, cnt = 0;
+    if (r < nrows) {
+      const int z = zmin + r / nys, y = ymin + r % nys;
+      const float zlo = g.oz + (float)z * g.h, ylo = g.oy + (float)y * g.h;
+      const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
+      const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
+      const float m2 = (gz * gz + gy * gy) * 0.999999f;
+      if (m2 <= gate_d2) {
+        const float rr = sqrtf(gate_d2 - m2) * 1.000001f + s2;
+        int xlo = (int)floorf((q.x - rr - g.ox) * g.inv_h);
+        int xhi = (int)floorf((q.x + rr - g.ox) * g.inv_h);
+        xlo = max(xlo, 0);
+        xhi = min(xhi, g.nx - 1);
+        if (xlo <= xhi) {
+          const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+          s = __ldg(cell_start + row + xlo);
+          cnt = __ldg(cell_start + row + xhi + 1) - s;
+        }
+      }
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(FULL, incl, lo + step - 1);
+        if (v <= c) lo += step;
+      }
+      lo = min(lo, 31);
+      const uint32_t row_s = __shfl_sync(FULL, s, lo);
+      const uint32_t row_incl = __shfl_sync(FULL, incl, lo);
+      const uint32_t row_cnt = __shfl_sync(FULL, cnt, lo);
+      if (c < total) {
+        const float4 p = __ldg(map_sorted + (row_s + (c - (row_incl - row_cnt))));
+        t.offer(l2_simple(q, p), __float_as_int(p.w));
+      }
+    }
+  }
+  // FZ_K + 1 smallest heads over the lanes, popped from their owners' lists
+  const unsigned gbits = __float_as_uint(gate_d2);
+  u64 res[FZ_K + 1];
+#pragma unroll
+  for (int k = 0; k <= FZ_K; ++k) {
+    const u64 m = warp_min_u64(t.k0);
+    res[k] = m;
+    const unsigned owners = __ballot_sync(FULL, t.k0 == m);
+    if (lane == __ffs(owners) - 1) { t.k0 = t.k1; t.k1 = t.k2; t.k2 = t.k3; t.k3 = t.k4; t.k4 = ~0ull; }
+  }
+  float rj = t.rej;  // best candidate a lane saw but dropped (its own 6th or worse, or beyond the gate)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rj = fminf(rj, __shfl_xor_sync(FULL, rj, o));
+#pragma unroll
+  for (int k = 0; k < FZ_K; ++k) out[k] = ((unsigned)(res[k] >> 32) < gbits) ? res[k] : ~0ull;
+  const float d9 = ((unsigned)(res[FZ_K] >> 32) < gbits) ? __uint_as_float((unsigned)(res[FZ_K] >> 32)) : gate_d2;
+  lb2 = fminf(fminf(gate_d2, rj), d9);
+  const float dn = ((unsigned)(res[5] >> 32) < gbits) ? __uint_as_float((unsigned)(res[5] >> 32)) : FLT_MAX;
+  d6 = fminf(dn, rj);
+}
+
 // shared-memory carve-up: the main phase and the leftover phase never overlap in time
 struct FzMainSmem {
-  int res_id[5][FZ_THREADS];      // the five neighbours of every slot of the chunk
-  float bound[FZ_THREADS];        // search request: > 0 seeded bound, 0 phase-1 gate, -1 straight to the leftovers, -2 none
-  float rows[FZ_THREADS][8];      // Jacobian row, rhs, accepted flag
-  unsigned char res_meta[FZ_THREADS];  // bit0 found, bit1 tie
-  unsigned char list[FZ_THREADS];      // slots queued for the search step, slot order
-  unsigned char llist[FZ_THREADS];     // slots the search could not settle (leftovers), list order
+  float rows[FZ_THREADS][8];               // Jacobian row, rhs, accepted flag
+  unsigned char llist[FZ_WARPS][32];       // per warp: slots deferred to the grid-wide leftover phase
+  int nl[FZ_WARPS];
 };
 struct FzLeftSmem {
   int off[FZ_MAXCHUNKS + 1];
@@ -245,11 +331,32 @@ union FzSmem {
   FzLeftSmem l;
 };
 
+// Full-gate search of a point the phase-1 gate could not settle, warp-cooperative, in two stages: most such points
+// have their five neighbours within 0.7 m, so a first pass over that ball usually settles them (a quarter of the rows
+// and candidates of the 1.25 m ball); only the rest walk the extended gate.  On return t holds the five nearest map
+// points closer than sqrt(r2) (ascending), r2 = the squared radius that was enumerated completely, and t.rej the
+// best distance among everything else that was visited.
+constexpr float FZ_LEFT_STAGE1 = 0.7f;
+__device__ __forceinline__ void fz_leftover_search(const float4 q, const GridParams& g, const float ge2,
+                                                   const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start,
+                                                   const int lane, Top5& t, float& r2) {
+  r2 = FZ_LEFT_STAGE1 * FZ_LEFT_STAGE1;
+  if (r2 < g.gate_d2) {
+    warp_knn5(q, g, r2, map_sorted, cell_start, lane, t, r2);
+    if (t.d(t.k4) < r2) return;  // five points inside the ball, all of it enumerated: exact
+  }
+  r2 = ge2;
+  warp_knn5(q, g, ge2, map_sorted, cell_start, lane, t, ge2);
+}
+
 // what a leftover search leaves behind for the next iteration: the candidate set (its five neighbours), the bound
-// (everything else it visited was >= rej away, everything it did not visit is beyond the extended gate) and the
-// hopeless marker
+// (everything else it visited was >= rej away, everything it did not visit is beyond the enumerated radius) and, for
+// a point with fewer than five map points inside the gate, the generalised hopeless marker: its 5th-nearest map
+// point is sqrt(d5) > 1 m away (or beyond the extended gate), so as long as the point has moved less than
+// sqrt(d5) - 1 m (minus 1 mm for rounding) since then it still cannot have five neighbours within the gate and
+// surfOptimization drops it (:1641) — no search needed.  Exact (triangle inequality), not heuristic.
 __device__ __forceinline__ void fz_store_leftover(const FusedArgs& A, const int mine, const float4 sel, const Top5& t,
-                                                  const int n_ext, const float ge2, const bool found) {
+                                                  const float r2, const bool found) {
   A.prev_nn[mine] = found ? t.i(t.k0) : -1;
   A.prev_nn[(size_t)A.nq + mine] = t.i(t.k1);
   A.prev_nn[2 * (size_t)A.nq + mine] = t.i(t.k2);
@@ -257,29 +364,44 @@ __device__ __forceinline__ void fz_store_leftover(const FusedArgs& A, const int 
   A.prev_nn[4 * (size_t)A.nq + mine] = t.i(t.k4);
 #pragma unroll
   for (int j = 5; j < FZ_K; ++j) A.prev_nn[(size_t)j * A.nq + mine] = -1;
-  A.prev_lb[mine] = sqrtf(fminf(t.rej, ge2)) * (1.f - FZ_REL);
-  const bool hopeless = !found && n_ext < 5;
-  A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, hopeless ? 1.f : 0.f);
+  A.prev_lb[mine] = sqrtf(fminf(t.rej, r2)) * (1.f - FZ_REL);
+  // d(k4) = the 5th-nearest distance^2 if five points lie inside the enumerated ball, else the ball's radius^2
+  const float margin = found ? 0.f : sqrtf(t.d(t.k4)) * (1.f - FZ_REL) - sqrtf(A.g.gate_d2) - 1e-3f;
+  A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, margin > 0.f ? margin : 0.f);
 }
 
-// sum of `nrows` partial rows (S2M_SUMS doubles each) in a fixed order: warp w takes rows w, w+8, ... with eight
-// independent accumulators (eight 256-byte loads in flight per warp), then the warps are added in order.
+// sum of `nrows` partial rows (S2M_SUMS doubles each) in a fixed order: warp w takes rows w, w+8, ... with sixteen
+// independent accumulators (sixteen 256-byte loads in flight per warp: the pass is L2-latency bound), added pairwise,
+// then the warps are added in order.
 // Result: lane l of warp 0 returns sum[l]; every thread must call it.
 __device__ __forceinline__ double fz_reduce_rows(const double* __restrict__ rows, const int nrows, double (*red)[S2M_SUMS],
                                                  const int warp, const int lane) {
-  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  constexpr int W = FZ_WARPS;
+  constexpr int W = FZ_WARPS, U = 16;
+  double a[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) a[k] = 0.0;
   int b = warp;
-  for (; b + 7 * W < nrows; b += 8 * W) {
-    double v[8];
+  for (; b + (U - 1) * W < nrows; b += U * W) {
+    double v[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldcg(rows + (size_t)(b + k * W) * S2M_SUMS + lane);
+    for (int k = 0; k < U; ++k) v[k] = __ldcg(rows + (size_t)(b + k * W) * S2M_SUMS + lane);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += v[k];
+    for (int k = 0; k < U; ++k) a[k] += v[k];
   }
-  for (int k = 0; b < nrows; b += W, ++k) a[k] += __ldcg(rows + (size_t)b * S2M_SUMS + lane);
+  {
+    double v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = (b + k * W < nrows) ? __ldcg(rows + (size_t)(b + k * W) * S2M_SUMS + lane) : 0.0;
+#pragma unroll
+    for (int k = 0; k < U; ++k) a[k] += v[k];
+  }
+#pragma unroll
+  for (int o = U / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < o; ++k) a[k] += a[k + o];
+  }
   __syncthreads();
-  red[warp][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  red[warp][lane] = a[0];
   __syncthreads();
   double sum = 0.0;
   if (warp == 0) {
@@ -297,7 +419,7 @@ s2m_fused_kernel(const FusedArgs A) {
   __shared__ double red[FZ_WARPS][S2M_SUMS];
   __shared__ double s_sum[S2M_SUMS];
   __shared__ FinSmem s_fin;
-  __shared__ int s_chunk, s_wcnt[FZ_WARPS], s_wcnt2[FZ_WARPS], s_misc[4];
+  __shared__ int s_chunk, s_wcnt[FZ_WARPS], s_misc[4];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   LmDevState* const st = A.st;
@@ -318,6 +440,7 @@ s2m_fused_kernel(const FusedArgs A) {
   const RowAcc ra = row_acc_of(lane);
   const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;  // extended gate of the leftover search
   const float ge2 = ge * ge;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   for (int it = 0; it < max_iter; ++it) {
     unsigned long long* const probe = A.probe ? A.probe + it * FZ_PROBES : nullptr;
@@ -346,13 +469,15 @@ s2m_fused_kernel(const FusedArgs A) {
       if (c >= A.nchunks) break;
       const int base = c * FZ_THREADS;
       const int i = base + tid;
-      // ---- step 1: classify ----
-      float req = -2.f;
-      int n_seeded = 0, n_cert = 0;
-      unsigned char meta = 0;
-      if (i < A.nq) {
-        const float4 ori = A.scan[i];
-        const float4 sel = apply_T(sT, ori);
+      const bool in = i < A.nq;
+      // ---- step 1: classify (lane = point) ----
+      float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
+      float req = -2.f;  // > 0 seeded bound, 0 phase-1 gate, -1 straight to the leftovers, -2 nothing to search
+      int n0 = -1, n1 = -1, n2 = -1, n3 = -1, n4 = -1;  // the five neighbours, ascending (d2, index)
+      bool found = false, tie = false, seeded = false, cert = false;
+      if (in) {
+        ori = A.scan[i];
+        sel = apply_T(sT, ori);
         req = can_phase1 ? 0.f : -1.f;
         if (it > 0) {
           const int p0 = __ldcg(A.prev_nn + i);
@@ -360,8 +485,7 @@ s2m_fused_kernel(const FusedArgs A) {
             const float4 hr = __ldcg(A.hopeless + i);
             if (hr.w > 0.f) {
               const float dx = sel.x - hr.x, dy = sel.y - hr.y, dz = sel.z - hr.z;
-              const float lim = HOPELESS_MARGIN - 1e-3f;
-              if ((dx * dx + dy * dy + dz * dz) < lim * lim) req = -2.f;  // still cannot have 5 neighbours within the gate
+              if ((dx * dx + dy * dy + dz * dz) * (1.f + FZ_REL) < hr.w * hr.w) req = -2.f;  // still cannot have 5 neighbours within the gate
             }
           } else {
             u64 key[8];
@@ -381,7 +505,7 @@ s2m_fused_kernel(const FusedArgs A) {
             const float D5 = __uint_as_float((unsigned)(key[4] >> 32));
             const float bound = __uint_as_float(__float_as_uint(D5) + 1u);  // next float above: the seeds stay inside
             if (bound <= A.g.gate_d2) {
-              n_seeded = 1;
+              seeded = true;
               req = bound;
               // certificate: every map point outside the set was >= lb away from where this point stood when the
               // set was built (or last certified); it has moved by |sel - prev|
@@ -389,138 +513,147 @@ s2m_fused_kernel(const FusedArgs A) {
               const float move = sqrtf(l2_simple(sel, pv));
               const float L = __ldcg(A.prev_lb + i) - move * (1.f + FZ_REL) - 1e-7f;
               if (A.use_cert && L > 0.f && L * L * (1.f - FZ_REL) > D5) {
-                n_cert = 1;
+                cert = true;
                 req = -2.f;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) sm.m.res_id[j][tid] = (int)(unsigned)(key[j] & 0xffffffffull);
+                found = true;
+                n0 = (int)(unsigned)key[0]; n1 = (int)(unsigned)key[1]; n2 = (int)(unsigned)key[2];
+                n3 = (int)(unsigned)key[3]; n4 = (int)(unsigned)key[4];
                 const float d0 = __uint_as_float((unsigned)(key[0] >> 32)), d1 = __uint_as_float((unsigned)(key[1] >> 32));
                 const float d2 = __uint_as_float((unsigned)(key[2] >> 32)), d3 = __uint_as_float((unsigned)(key[3] >> 32));
                 const float d5 = __uint_as_float((unsigned)(key[5] >> 32));
-                const bool tie = d0 == d1 || d1 == d2 || d2 == d3 || d3 == D5 || (key[5] != ~0ull && D5 == d5);
-                meta = (unsigned char)(1 | (tie ? 2 : 0));
+                tie = d0 == d1 || d1 == d2 || d2 == d3 || d3 == D5 || (key[5] != ~0ull && D5 == d5);
                 A.prev_lb[i] = L * (1.f - FZ_REL);
               }
             }
           }
         }
       }
-      sm.m.res_meta[tid] = meta;
-      sm.m.bound[tid] = req;
-      const bool want = req > -2.f;
-      const unsigned wm = __ballot_sync(FULL, want);
-      if (lane == 0) s_wcnt[warp] = __popc(wm);
-      __syncthreads();
-      int ns = 0, woff = 0;
-#pragma unroll
-      for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) woff += s_wcnt[w]; ns += s_wcnt[w]; }
-      // search-heavy chunk (iterations 0 and 1): thread = point, no compaction; otherwise the requests are
-      // compacted so that the searching warps run with dense lanes
-      const bool direct = ns > FZ_DIRECT_MIN;
-      if (!direct) {
-        if (want) sm.m.list[woff + __popc(wm & ((1u << lane) - 1u))] = (unsigned char)tid;
-        __syncthreads();
-      }
       // ---- step 2: search ----
-      bool need2 = false;
-      int slot = -1;
-      if (direct) { if (want) slot = tid; }
-      else if (tid < ns) slot = sm.m.list[tid];
-      if (slot >= 0) {
-        const int qi = base + slot;
-        const float rq = sm.m.bound[slot];
-        need2 = true;
-        if (rq >= 0.f) {
-          const float4 sel = apply_T(sT, A.scan[qi]);
-          const bool seeded = rq > 0.f;
-          float gate_use = A.g.gate1_d2;
-          if (seeded) { const float r = sqrtf(rq) + FZ_SEED_MARGIN; gate_use = fmaxf(r * r, rq); }
-          TopN t;
-          grid_knn_topn(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
-          const float lim5 = seeded ? rq : A.g.gate1_d2;
-          need2 = !(t.d(4) < lim5);   // a seeded search always finds its five (the seeds are inside the bound)
-          if (!need2) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) sm.m.res_id[j][slot] = t.i(j);
-            const bool tie = t.d(0) == t.d(1) || t.d(1) == t.d(2) || t.d(2) == t.d(3) || t.d(3) == t.d(4) || t.d(4) == t.d(5);
-            sm.m.res_meta[slot] = (unsigned char)(1 | (tie ? 2 : 0));
-            // next iteration's candidate set and its bound: slots still holding the sentinel are empty
-            const unsigned gbits = __float_as_uint(gate_use);
-#pragma unroll
-            for (int j = 0; j < FZ_K; ++j) {
-              const bool real = !((unsigned)(t.k[j] >> 32) == gbits && (unsigned)t.k[j] == 0u);
-              A.prev_nn[(size_t)j * A.nq + qi] = real ? t.i(j) : -1;
-            }
-            A.prev_lb[qi] = sqrtf(t.worst()) * (1.f - FZ_REL);
-          }
-        }
-      }
-      // leftovers of this chunk, in search order
-      int nl = 0;
-      {
-        const unsigned fm = __ballot_sync(FULL, need2);
-        if (lane == 0) s_wcnt2[warp] = __popc(fm);
-        __syncthreads();
-        int off = 0;
-#pragma unroll
-        for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) off += s_wcnt2[w]; nl += s_wcnt2[w]; }
-        if (need2) sm.m.llist[off + __popc(fm & ((1u << lane) - 1u))] = (unsigned char)slot;
-      }
-      const bool deferred = nl > FZ_INPLACE;
-      if (nl > 0) {
-        __syncthreads();
-        if (!deferred) {
-          // a handful: one warp-cooperative full-gate search per warp, right here
-          if (warp < nl) {
-            const int ls = sm.m.llist[warp];
-            const int mine = base + ls;
-            const float4 sel = apply_T(sT, A.scan[mine]);
+      bool need2 = req == -1.f;
+      const bool want = req >= 0.f;
+      const unsigned wm = __ballot_sync(FULL, want);
+      if (wm) {
+        if (it == 0) {
+          // no candidate sets yet, and none built here would survive the first (large) step: the plain 5-nearest walk
+          if (want) {
             Top5 t;
-            const int n_ext = warp_knn5(sel, A.g, ge2, A.map_sorted, A.cell_start, lane, t);
-            if (lane == 0) {
-              const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641
-              fz_store_leftover(A, mine, sel, t, n_ext, ge2, found);
-              if (found) {
-                sm.m.res_id[0][ls] = t.i(t.k0); sm.m.res_id[1][ls] = t.i(t.k1); sm.m.res_id[2][ls] = t.i(t.k2);
-                sm.m.res_id[3][ls] = t.i(t.k3); sm.m.res_id[4][ls] = t.i(t.k4);
-                sm.m.res_meta[ls] = (unsigned char)(1 | (t.tie() ? 2 : 0));
+            grid_knn5(sel, A.g, A.g.gate1_d2, A.map_sorted, A.cell_start, t);
+            need2 = !(t.d(t.k4) < A.g.gate1_d2);
+            if (!need2) {
+              found = true; tie = t.tie();
+              n0 = t.i(t.k0); n1 = t.i(t.k1); n2 = t.i(t.k2); n3 = t.i(t.k3); n4 = t.i(t.k4);
+              A.prev_nn[i] = n0; A.prev_nn[(size_t)A.nq + i] = n1; A.prev_nn[2 * (size_t)A.nq + i] = n2;
+              A.prev_nn[3 * (size_t)A.nq + i] = n3; A.prev_nn[4 * (size_t)A.nq + i] = n4;
+#pragma unroll
+              for (int j = 5; j < FZ_K; ++j) A.prev_nn[(size_t)j * A.nq + i] = -1;
+              A.prev_lb[i] = sqrtf(t.d(t.k4)) * (1.f - FZ_REL);  // everything outside the five is at least this far
+            }
+          }
+        } else if (__popc(wm) > FZ_WCOOP_MAX) {
+          // many lanes: lane = point, the 9-nearest walk
+          if (want) {
+            const bool sd = req > 0.f;
+            float gate_use = A.g.gate1_d2;
+            if (sd) { const float r = sqrtf(req) + FZ_SEED_MARGIN; gate_use = fmaxf(r * r, req); }
+            TopN t;
+            grid_knn_topn(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+            need2 = !(t.d(4) < (sd ? req : A.g.gate1_d2));  // a seeded search always finds its five
+            if (!need2) {
+              found = true;
+              tie = t.d(0) == t.d(1) || t.d(1) == t.d(2) || t.d(2) == t.d(3) || t.d(3) == t.d(4) || t.d(4) == t.d(5);
+              n0 = t.i(0); n1 = t.i(1); n2 = t.i(2); n3 = t.i(3); n4 = t.i(4);
+              const unsigned gbits = __float_as_uint(gate_use);
+#pragma unroll
+              for (int j = 0; j < FZ_K; ++j) {
+                const bool real = !((unsigned)(t.k[j] >> 32) == gbits && (unsigned)t.k[j] == 0u);
+                A.prev_nn[(size_t)j * A.nq + i] = real ? t.i(j) : -1;
               }
+              A.prev_lb[i] = sqrtf(t.worst()) * (1.f - FZ_REL);
             }
           }
         } else {
-          if (tid < nl) A.left_list[(size_t)base + tid] = base + sm.m.llist[tid];
-          if (tid == 0) cta_deferred += nl;
+          // a few lanes: the warp serves them one by one, cooperatively
+          unsigned todo = wm;
+          while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float4 q;
+            q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j); q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
+            const float rq = __shfl_sync(FULL, req, j);
+            const bool sd = rq > 0.f;
+            float gate_use = A.g.gate1_d2;
+            if (sd) { const float r = sqrtf(rq) + FZ_SEED_MARGIN; gate_use = fmaxf(r * r, rq); }
+            u64 k[FZ_K];
+            float lb2, d6;
+            warp_knn_set(q, A.g, gate_use, A.map_sorted, A.cell_start, lane, k, lb2, d6);
+            if (lane == j) {
+              const float e0 = __uint_as_float((unsigned)(k[0] >> 32)), e1 = __uint_as_float((unsigned)(k[1] >> 32));
+              const float e2 = __uint_as_float((unsigned)(k[2] >> 32)), e3 = __uint_as_float((unsigned)(k[3] >> 32));
+              const float e4 = __uint_as_float((unsigned)(k[4] >> 32));
+              need2 = !(k[4] != ~0ull && e4 < (sd ? rq : A.g.gate1_d2));
+              if (!need2) {
+                found = true;
+                tie = e0 == e1 || e1 == e2 || e2 == e3 || e3 == e4 || e4 == d6;
+                n0 = (int)(unsigned)k[0]; n1 = (int)(unsigned)k[1]; n2 = (int)(unsigned)k[2];
+                n3 = (int)(unsigned)k[3]; n4 = (int)(unsigned)k[4];
+#pragma unroll
+                for (int m = 0; m < FZ_K; ++m) A.prev_nn[(size_t)m * A.nq + i] = k[m] != ~0ull ? (int)(unsigned)k[m] : -1;
+                A.prev_lb[i] = sqrtf(lb2) * (1.f - FZ_REL);
+              }
+            }
+          }
         }
       }
-      if (tid == 0) A.chunk_nleft[c] = deferred ? nl : 0;
-      __syncthreads();
-      // ---- step 3: plane fit + Jacobian row (thread = point) ----
+      // ---- step 3: leftovers (points the phase-1 gate could not settle) ----
+      const unsigned lm = __ballot_sync(FULL, need2);
+      const int nl = __popc(lm);
+      const bool deferred = nl > FZ_INPLACE;
+      if (nl > 0) {
+        if (!deferred) {
+          unsigned todo = lm;
+          while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float4 q;
+            q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j); q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
+            Top5 t;
+            float r2;
+            fz_leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, t, r2);
+            if (lane == j) {
+              found = t.d(t.k4) < A.g.gate_d2;  // :1641
+              fz_store_leftover(A, i, sel, t, r2, found);
+              if (found) { tie = t.tie(); n0 = t.i(t.k0); n1 = t.i(t.k1); n2 = t.i(t.k2); n3 = t.i(t.k3); n4 = t.i(t.k4); }
+            }
+          }
+        } else if (need2) {
+          sm.m.llist[warp][__popc(lm & lt_mask)] = (unsigned char)tid;
+        }
+      }
+      if (lane == 0) sm.m.nl[warp] = deferred ? nl : 0;
+      // ---- step 4: plane fit + Jacobian row ----
       float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float rhs = 0.f;
-      bool flag = false, tie = false;
-      if (i < A.nq) {
-        const unsigned char mt = sm.m.res_meta[tid];
+      bool flag = false;
+      if (in) {
         float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-        int nid[5] = {-1, -1, -1, -1, -1};
-        float nd2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        const bool pending = deferred && sm.m.bound[tid] > -2.f && !(mt & 1);  // finished by the leftover phase
-        if (mt & 1) {
-          const float4 ori = A.scan[i];
-          const float4 sel = apply_T(sT, ori);
+        float nd2[5] = {A.g.gate_d2, A.g.gate_d2, A.g.gate_d2, A.g.gate_d2, A.g.gate_d2};
+        if (found) {
           float4 nbr[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) { nid[j] = sm.m.res_id[j][tid]; nbr[j] = __ldg(A.map4 + nid[j]); }
+          nbr[0] = __ldg(A.map4 + n0); nbr[1] = __ldg(A.map4 + n1); nbr[2] = __ldg(A.map4 + n2);
+          nbr[3] = __ldg(A.map4 + n3); nbr[4] = __ldg(A.map4 + n4);
           flag = plane_residual(ori, sel, nbr, coeff);
-          tie = (mt & 2) != 0;
           if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
           if (flag) jacobian_row(sTrig, ori, coeff, row, rhs);
           if (A.dbg.nn_d2) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) nd2[j] = l2_simple(sel, nbr[j]);
           }
+        } else {
+          tie = false;
         }
-        if (!pending) {
-          if (A.dbg.nn_idx) { int* o = A.dbg.nn_idx + (size_t)i * 5; for (int j = 0; j < 5; ++j) o[j] = nid[j]; }
-          if (A.dbg.nn_d2) { float* o = A.dbg.nn_d2 + (size_t)i * 5; for (int j = 0; j < 5; ++j) o[j] = (mt & 1) ? nd2[j] : A.g.gate_d2; }
+        if (!(deferred && need2)) {  // deferred points are written by the leftover phase
+          if (A.dbg.nn_idx) { int* o = A.dbg.nn_idx + (size_t)i * 5; o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; }
+          if (A.dbg.nn_d2) { float* o = A.dbg.nn_d2 + (size_t)i * 5; for (int j = 0; j < 5; ++j) o[j] = nd2[j]; }
           if (A.dbg.coeff) A.dbg.coeff[i] = coeff;
           if (A.dbg.flag) A.dbg.flag[i] = flag ? 1 : 0;
           if (A.dbg.tie) A.dbg.tie[i] = tie ? 1 : 0;
@@ -531,9 +664,9 @@ s2m_fused_kernel(const FusedArgs A) {
       sm.m.rows[tid][6] = rhs;
       sm.m.rows[tid][7] = flag ? 1.f : 0.f;
       const int w_ties = __popc(__ballot_sync(FULL, flag && tie));
-      const int w_seed = __popc(__ballot_sync(FULL, n_seeded != 0));
-      const int w_cert = __popc(__ballot_sync(FULL, n_cert != 0));
-      __syncthreads();
+      const int w_seed = __popc(__ballot_sync(FULL, seeded));
+      const int w_cert = __popc(__ballot_sync(FULL, cert));
+      __syncwarp();
       {
         double acc = 0.0;
         if (ra.live) {
@@ -546,7 +679,7 @@ s2m_fused_kernel(const FusedArgs A) {
         if (lane == 28) acc = (double)w_ties;
         if (lane == 29) acc = (double)w_seed;
         if (lane == 30) acc = (double)w_cert;
-        if (lane == 31) acc = warp == 0 ? (double)nl : 0.0;
+        if (lane == 31) acc = (double)nl;
         red[warp][lane] = acc;
       }
       __syncthreads();
@@ -555,6 +688,13 @@ s2m_fused_kernel(const FusedArgs A) {
 #pragma unroll
         for (int k = 0; k < FZ_WARPS; ++k) sum += red[k][tid];
         A.chunk_rows[(size_t)c * S2M_SUMS + tid] = sum;
+      }
+      {  // the chunk's deferred leftovers, warp by warp, into its segment of the global list
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < FZ_WARPS; ++w) { if (w < warp) off += sm.m.nl[w]; tot += sm.m.nl[w]; }
+        if (lane < sm.m.nl[warp]) A.left_list[(size_t)base + off + lane] = base + sm.m.llist[warp][lane];
+        if (tid == 0) { A.chunk_nleft[c] = tot; cta_deferred += tot; }
       }
       __syncthreads();
     }
@@ -671,14 +811,15 @@ s2m_fused_kernel(const FusedArgs A) {
           if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
           Top5 t;
           t.init(A.g.gate_d2);
-          int my_ext = 0;
+          float my_r2 = ge2;
           for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
             float4 q;
             q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j);
             q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
             Top5 tj;
-            const int n_ext = warp_knn5(q, A.g, ge2, A.map_sorted, A.cell_start, lane, tj);
-            if (lane == j) { t = tj; my_ext = n_ext; }
+            float r2;
+            fz_leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, tj, r2);
+            if (lane == j) { t = tj; my_r2 = r2; }
           }
           if (mine >= 0) {
             const bool found = t.d(t.k4) < A.g.gate_d2;  // :1641
@@ -692,7 +833,7 @@ s2m_fused_kernel(const FusedArgs A) {
               if (!flag) coeff = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (flag) jacobian_row(sTrig, ori, coeff, row, rhs);
-            fz_store_leftover(A, mine, sel, t, my_ext, ge2, found);
+            fz_store_leftover(A, mine, sel, t, my_r2, found);
             if (A.dbg.nn_idx) {
               int* o = A.dbg.nn_idx + (size_t)mine * 5;
               o[0] = found ? t.i(t.k0) : -1; o[1] = found ? t.i(t.k1) : -1; o[2] = found ? t.i(t.k2) : -1;

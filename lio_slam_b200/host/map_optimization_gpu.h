@@ -81,7 +81,8 @@ class mapOptimization {
   float surroundingKeyframeSearchRadius = 50.0f, surroundingKeyframeDensity = 2.0f;
   float surroundingkeyframeAddingDistThreshold = 1.0f, surroundingkeyframeAddingAngleThreshold = 0.2f;
   bool fetchLocalMap = false;      // copy laserCloudSurfFromMapDS back (it is only needed for publishing)
-  bool selectKeyPosesOnDevice = false;  // extractNearby through liogpu_extract_nearby (pays off on long runs)
+  bool selectKeyPosesOnDevice = false;  // extractNearby through liogpu_extract_nearby whatever the number of key poses
+  int selectKeyPosesOnDeviceAbove = 3000;  // ... and automatically above this many key poses (measured crossover)
   // publishLocalMap settings (utility.h:219-229) and its output cloud (tempCloud, :2541)
   int localMapKeyFramesNumber = 30;
   liogpu_local_map_params localMapParams;

@@ -84,9 +84,10 @@ EXPORTS = ["liogpu_abi_version", "liogpu_default_params", "liogpu_create", "liog
            "liogpu_build_local_map", "liogpu_set_local_map", "liogpu_local_map_size", "liogpu_scan2map",
            "liogpu_downsample_scan2map", "liogpu_surf_optimization", "liogpu_last_gpu_ms", "liogpu_launch_count",
            "liogpu_stream", "liogpu_resident_size", "liogpu_default_local_map_params", "liogpu_publish_local_map", "liogpu_merge_keyframes", "liogpu_default_icp_params", "liogpu_icp_align", "liogpu_make_scancontext", "liogpu_extract_nearby",
-           "liogpu_scan2map_trace", "liogpu_voxel_tile"]
+           "liogpu_scan2map_trace", "liogpu_voxel_tile", "liogpu_upload_scan_async", "liogpu_fetch_result"]
 
 RESIDENT = "resident"   # LIOGPU_DEVICE_RESIDENT: the cloud the context kept in HBM (include/liogpu.h)
+UPLOADED = "uploaded"   # LIOGPU_UPLOADED_SCAN: the sweep liogpu_upload_scan_async put on its way
 
 _lib = None
 
@@ -129,6 +130,8 @@ def load_library() -> C.CDLL:
     lib.liogpu_set_local_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.liogpu_merge_keyframes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                            C.c_int, C.POINTER(C.c_int)]
+    lib.liogpu_upload_scan_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.liogpu_fetch_result.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.liogpu_voxel_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
                                       C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(TileInfo)]
     lib.liogpu_make_scancontext.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
@@ -185,6 +188,8 @@ def _cloud_args(cloud):
     """-> (pointer:int, n, stride, keepalive)"""
     if isinstance(cloud, str) and cloud == RESIDENT:
         return 1, 0, 16, None
+    if isinstance(cloud, str) and cloud == UPLOADED:
+        return 2, 0, 16, None
     if isinstance(cloud, tuple):
         ptr, n, stride = cloud
         return int(ptr), int(n), int(stride), None
@@ -307,11 +312,9 @@ class LioGpu:
             out = np.empty((int(cap or 1), 4), np.float32)
             st = self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
                                                  C.c_float(leaf), C.byref(n_map), out.ctypes.data, 16, out.shape[0])
-            if st == E_CAPACITY:  # retry with the reported size
+            if st == E_CAPACITY:  # the map is built and installed: copy it out without rebuilding
                 out = np.empty((n_map.value, 4), np.float32)
-                st = self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
-                                                     C.c_float(leaf), C.byref(n_map), out.ctypes.data, 16,
-                                                     out.shape[0])
+                st = self.lib.liogpu_fetch_result(self.h, out.ctypes.data, 16, out.shape[0], C.byref(n_map))
             self._check(st)
             return out[: n_map.value].copy(), st
         st = self._check(self.lib.liogpu_build_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
@@ -326,13 +329,10 @@ class LioGpu:
         info = TileInfo()
         n_out = C.c_int(0)
         if out is None:
-            st = self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf), tile,
-                                            n_tiles, None, 16, 0, C.byref(n_out), C.byref(info))
-            self._check(st)
-            host = np.empty((max(n_out.value, 1), 4), np.float32)
             st = self._check(self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf),
-                                                        tile, n_tiles, host.ctypes.data, 16, host.shape[0], C.byref(n_out),
-                                                        C.byref(info)))
+                                                        tile, n_tiles, None, 16, 0, C.byref(n_out), C.byref(info)))
+            host = np.empty((max(n_out.value, 1), 4), np.float32)
+            self._check(self.lib.liogpu_fetch_result(self.h, host.ctypes.data, 16, host.shape[0], C.byref(n_out)))
             res = host[: n_out.value].copy()
         else:
             ptr, cap = out
@@ -355,11 +355,11 @@ class LioGpu:
         st = self.lib.liogpu_publish_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
                                                pose_now.ctypes.data, C.byref(prm), out.ctypes.data, 16, out.shape[0],
                                                C.byref(n_out), C.byref(info))
-        if st == E_CAPACITY:  # retry with the reported size
+        if st == E_CAPACITY:  # the cloud exists on the device: copy it out without recomputing
             out = np.empty((n_out.value, 4), np.float32)
-            st = self.lib.liogpu_publish_local_map(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
-                                                   pose_now.ctypes.data, C.byref(prm), out.ctypes.data, 16,
-                                                   out.shape[0], C.byref(n_out), C.byref(info))
+            st = self.lib.liogpu_fetch_result(self.h, out.ctypes.data, 16, out.shape[0], C.byref(n_out))
+            if st == OK and info.leaf_overflow:
+                st = W_LEAF_OVERFLOW
         self._check(st)
         d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "reserved"}
         return out[: n_out.value].copy(), d, st
@@ -375,8 +375,7 @@ class LioGpu:
                                              out.ctypes.data, 16, out.shape[0], C.byref(n_out))
         if st == E_CAPACITY:
             out = np.empty((n_out.value, 4), np.float32)
-            st = self.lib.liogpu_merge_keyframes(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0],
-                                                 C.c_float(leaf), out.ctypes.data, 16, out.shape[0], C.byref(n_out))
+            st = self.lib.liogpu_fetch_result(self.h, out.ctypes.data, 16, out.shape[0], C.byref(n_out))
         self._check(st)
         return out[: n_out.value].copy(), st
 
@@ -415,6 +414,11 @@ class LioGpu:
                                                         C.c_float(radius), C.c_float(density), ids.ctypes.data, ids.shape[0],
                                                         C.byref(n_ids)))
         return ids[: n_ids.value].copy(), st
+
+    def upload_scan_async(self, cloud) -> None:
+        """liogpu_upload_scan_async: the buffer must stay alive until the call that consumes UPLOADED returns."""
+        ptr, n, stride, keep = _cloud_args(cloud)
+        self._check(self.lib.liogpu_upload_scan_async(self.h, ptr, n, stride))
 
     def set_local_map(self, cloud) -> None:
         ptr, n, stride, keep = _cloud_args(cloud)

@@ -118,3 +118,33 @@ def test_sequence_gpu_equals_oracle(oracle, world):
     poses = np.array([p for p, _, _ in got])
     assert np.abs(poses[:, 3:] - gts[:, 3:]).max() < 0.08
     print("bit-equal poses:", sum(np.array_equal(a[0], b[0]) for a, b in zip(got, want)), "of", n)
+
+
+@pytest.mark.parametrize("on_device_nearby", [0, 1])
+def test_kitti_sequence_replay_matches_oracle_scan_by_scan(oracle, world, on_device_nearby):
+    """BASELINE configs[4] at test size: ONE synthetic 64-beam sequence (kitti.yaml: downsampleRate 2, point_filter_num 5,
+    leaves 0.4 / 0.5), 56 sweeps, through the host mirror's full per-scan path (liorf_replay.cpp: deskew kept in HBM ->
+    extractNearby -> extractCloud -> downsample + registration -> keyframe from the resident cloud) against the same
+    path driven with the CPU oracle, scan by scan."""
+    import torch
+    from lio_slam_b200 import replay, synth_torch
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from replay_oracle import replay_sequence_oracle
+    n = 56
+    seq = synth_torch.make_sequence(world, 64, n, seed=5, device=torch.device("cuda", 0), step=0.35)
+    prm = replay.kitti_params()
+    got_pose, got_it, got_nds, st = replay.replay_sequence(prm, seq, select_key_poses_on_device=on_device_nearby)
+    want_pose, want_it, want_nds, wst = replay_sequence_oracle(oracle, seq, threads=8)
+    assert st["scans"] == n and st["registered"] == n - 1
+    assert st["keyframes"] == wst["keyframes"] >= 10
+    assert np.array_equal(got_nds, want_nds)                      # deskew + decimation + VoxelGrid: same clouds
+    assert np.array_equal(got_it, want_it), (got_it, want_it)     # same iteration counts, scan by scan
+    assert np.abs(got_pose[:, :3] - want_pose[:, :3]).max() <= 1e-5
+    assert np.abs(got_pose[:, 3:] - want_pose[:, 3:]).max() <= 1e-4
+    gts = seq["gts"]
+    assert np.abs(got_pose[:, 3:] - gts[:, 3:]).max() < 0.1       # and it actually tracks the drive
+    print(f"on_device_nearby={on_device_nearby}: bit-equal poses {int((got_pose.view(np.uint32) == want_pose.view(np.uint32)).all(axis=1).sum())} of {n}; "
+          f"keyframes {st['keyframes']}, map rebuilds {st['map_rebuilds']}, wall {st['wall_ms'] / n:.3f} ms/scan "
+          f"(deskew {st['deskew_ms'] / n:.3f}, nearby+map {st['nearby_ms'] / n:.3f}, register {st['register_ms'] / n:.3f}, "
+          f"keyframe {st['keyframe_ms'] / n:.3f}), launches/scan {st['gpu_launches'] / n:.0f}, oracle {wst['wall_ms'] / n:.1f} ms/scan")
