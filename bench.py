@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one scan-to-map registration (liogpu_scan2map: the whole Gauss-Newton loop of
-scan2MapOptimization, mapOptmization.cpp:1848-1859, ONE kernel launch) of one synthetic sweep against a resident local map.
+scan2MapOptimization, mapOptmization.cpp:1848-1859, entirely on the device) of one synthetic sweep against a resident local map.
 Headline workload (BASELINE.json configs[2], the one the north_star target is quoted on):
     128-beam sweep, 230,400 points, all used as queries, vs a 500,000-point local map (leaf 0.2).
 `value`  : registrations/s with the sweep already in HBM (packed float4), device time by CUDA events on the
@@ -244,13 +244,13 @@ def bench_registration(torch, g, name, map4, scans, guesses, steps, warmup, flus
         g.set_local_map((dev_map.data_ptr(), map4.shape[0], 16))
         idx_ms.append(1e3 * (time.perf_counter() - t0))
     return dict(dev_ms=dev_ms, loop_ms=loop_ms, iters=iters, e2e_ms=e2e_ms, launches=launches, nqs=nqs,
-                index_build_ms=float(np.median(idx_ms[1:])), dev_scans=dev_scans)
+                index_build_ms=float(np.median(idx_ms[1:])), dev_scans=dev_scans, kernel_launches=info["kernel_launches"])
 
 
-def profile_phases(torch, LioGpu, default_params, w, map4, dev_scans, nqs, guesses, flush, local_rank, n):
-    """untimed pass with the library's on-device phase probes (profile_kernels): phase durations per iteration"""
+def profile_phases(torch, LioGpu, default_params, w, map4, dev_scans, nqs, guesses, flush, local_rank, n, **over):
+    """untimed pass with the library's per-kernel events / on-device phase probes (profile_kernels)"""
     gp = LioGpu(default_params(device=local_rank, n_scan=w["beams"], horizon_scan=w["cols"],
-                               surrounding_keyframe_map_leaf_size=w["map_leaf"], profile_kernels=1))
+                               surrounding_keyframe_map_leaf_size=w["map_leaf"], profile_kernels=1, **over))
     gp.set_local_map(map4)
     kern = {"main_ms": 0.0, "rest_ms": 0.0, "tail_ms": 0.0, "iters": 0, "loop_ms": 0.0, "certified": [], "leftovers": [],
             "main_us_hist": None}
@@ -269,6 +269,34 @@ def profile_phases(torch, LioGpu, default_params, w, map4, dev_scans, nqs, guess
                 kern["certified_hist"] = inf["certified_hist"].tolist()
     gp.close()
     return kern
+
+
+def loop_ab(torch, LioGpu, default_params, w, map4, dev_scans, nqs, guesses, flush, local_rank, n=12):
+    """A/B of the two implementations of the LM loop on this workload (device-resident sweeps, L2 flushed)"""
+    out = {}
+    for label, over in (("two_kernel", dict(s2m_path=1)), ("fused_one_launch", dict(s2m_path=2)),
+                        ("fused_no_certificate", dict(s2m_path=2, s2m_no_certificate=1))):
+        gx = LioGpu(default_params(device=local_rank, n_scan=w["beams"], horizon_scan=w["cols"],
+                                   surrounding_keyframe_map_leaf_size=w["map_leaf"], **over))
+        gx.set_local_map(map4)
+        ms, it, poses = [], [], []
+        for s in range(n + 3):
+            k = s % len(dev_scans)
+            flush.fill_(s & 0xff)
+            torch.cuda.synchronize()
+            pose, _, inf = gx.scan2map((dev_scans[k].data_ptr(), nqs[k], 16), guesses[k], max_iter=MAX_ITER)
+            if s >= 3:
+                ms.append(inf["gpu_ms"]); it.append(inf["iterations"])
+            if s < len(dev_scans):
+                poses.append(pose.tolist())
+        gx.close()
+        out[label] = {"loop_ms_per_registration": float(np.mean(ms)), "iteration_us": 1e3 * float(np.sum(ms)) / float(np.sum(it)),
+                      "mean_lm_iterations": float(np.mean(it)), "kernel_launches_per_registration": int(inf["kernel_launches"]),
+                      "_poses": poses}
+    ref = out["two_kernel"].pop("_poses")
+    for label in ("fused_one_launch", "fused_no_certificate"):
+        out[label]["poses_bit_equal_to_two_kernel"] = out[label].pop("_poses") == ref
+    return out
 
 
 def bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank, steps=10):
@@ -503,6 +531,9 @@ def main():
     clocks = sampler.stop() if sampler else None
     kern = profile_phases(torch, LioGpu, default_params, w, map4, r["dev_scans"], r["nqs"], guesses, flush, local_rank,
                           min(args.steps, 16))
+    ab = None
+    if rank == 0 and world_size == 1 and not args.no_extras:
+        ab = loop_ab(torch, LioGpu, default_params, w, map4, r["dev_scans"], r["nqs"], guesses, flush, local_rank)
     g.close()
 
     tot_ms = float(np.sum(r["dev_ms"])); tot_e2e = float(np.sum(r["e2e_ms"]))
@@ -556,42 +587,47 @@ def main():
     total_regs = args.steps * world_size
     value = total_regs / (tot_ms * 1e-3)
     e2e_value = total_regs / (tot_e2e * 1e-3)
-    # roofline of the dominant kernel.  The whole LM loop is ONE launch (s2m_fused_kernel); its algorithmic bytes are
-    # 96 B per sweep point per executed iteration (16 B query + 5 x 16 B neighbours) and its duration is the
-    # CUDA-event time of the launch, so achieved = 96 B x n_query / (launch time / iterations).
+    # roofline of the dominant kernel: algorithmic bytes = 96 B per sweep point per Gauss-Newton iteration (16 B query +
+    # 5 x 16 B neighbours), duration = the average CUDA-event time of a launch of that kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     it_total = float(np.sum(r["iters"]))
-    launch_us = 1e3 * float(np.mean(r["loop_ms"]))
     iteration_us = 1e3 * float(np.sum(r["loop_ms"])) / it_total
     mean_iters = float(np.mean(r["iters"]))
-    achieved = 96.0 * nq * mean_iters / (launch_us * 1e-6) / 1e9
     traffic, traffic_note = None, "not captured"
+    main_us = 1e3 * kern["main_ms"] / max(kern["iters"], 1)
+    rest_us = 1e3 * kern["rest_ms"] / max(kern["iters"], 1)
+    if r["kernel_launches"] > 1:
+        # two launches per iteration: the dominant kernel is s2m_main_kernel (search + plane fit + Jacobian) when it
+        # runs (dense map), else s2m_left_kernel; average launch duration from CUDA events around every launch
+        dom, launch_us = ("s2m_main_kernel", main_us) if main_us >= rest_us else ("s2m_left_kernel", rest_us)
+        alg_bytes = 96 * nq
+    else:
+        # the whole loop is ONE launch (s2m_fused_kernel): 96 B per sweep point per executed iteration
+        dom, launch_us = "s2m_fused_kernel", 1e3 * float(np.mean(r["loop_ms"]))
+        alg_bytes = int(96 * nq * mean_iters)
+    achieved = alg_bytes / (launch_us * 1e-6) / 1e9
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("s2m_fused_kernel")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(dom)
         if tr and tr.get("n_query") == nq and tr.get("workload") == name:
             traffic = tr["dram_bytes_per_launch"]
-            traffic_note = ("ncu --set full capture of the same command (cold-cache, serialised replay: every launch starts with "
-                            "an empty L2, as the L2-flushed bench step does); dram__bytes_read.sum + dram__bytes_write.sum per launch")
+            traffic_note = ("ncu --set full capture of the same command: a cold-cache, serialised replay (ncu flushes the caches before "
+                            "every launch, like the L2-flushed first iteration of a bench step; the later iterations of a live step "
+                            "find the map and the sweep in L2 and read almost nothing from DRAM)")
     except Exception:
         pass
-    main_us = 1e3 * kern["main_ms"] / max(kern["iters"], 1)
-    roofline = {"bound": "hbm", "kernel": "s2m_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(96 * nq * mean_iters), "avg_launch_us": launch_us,
-                "iterations_per_launch": mean_iters, "iteration_us": iteration_us,
-                "search_fit_phase_us_per_iteration": main_us,
-                "reduction_tail_us_per_iteration": 1e3 * kern["rest_ms"] / max(kern["iters"], 1),
-                "search_fit_phase_frac": 96.0 * nq / (main_us * 1e-6) / 1e9 / peak if main_us > 0 else None,
-                "one_registration": {"search_fit_us": kern.get("main_us_hist"), "rest_us": kern.get("rest_us_hist"),
-                                     "certified_points": kern.get("certified_hist")},
-                "note": "achieved = 96 B x n_query x iterations / CUDA-event time of the ONE launch that runs the whole loop; "
-                        "search_fit_phase_* isolates the kNN + plane-fit + Jacobian phase (on-device %globaltimer probes, untimed "
-                        "pass) — the quantity round 1 reported for s2m_main_kernel.  The working set (map 16 MB + sweep 3.7 MB) is "
-                        "L2-resident, so the HBM fraction is structurally small: the kernel is instruction-issue bound"}
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": launch_us,
+                "kernel_launches_per_registration": int(r["kernel_launches"]),
+                "iteration_us": iteration_us, "search_fit_us_per_iteration": main_us,
+                "leftover_reduction_tail_us_per_iteration": rest_us,
+                "note": "achieved = algorithmic bytes (96 B per sweep point per iteration: 16 B query + 5 x 16 B neighbours, SURVEY §8d) "
+                        "/ average CUDA-event duration of a launch of the dominant kernel.  The working set (map 16 MB + sweep "
+                        "3.7 MB) is L2-resident, so the HBM fraction is structurally small: the kernel is instruction-issue bound"}
     cb = None
     like = None
     if not args.no_cpu_baseline and world_size == 1:
@@ -616,6 +652,8 @@ def main():
             "gpu_launches": launches, "mean_lm_iterations": mean_iters,
             "loop_ms_per_step": float(np.mean(r["loop_ms"])), "wall_s_region1": wall_s,
             "roofline": roofline, "cpu_baseline": cb, "like_for_like": like, "clocks": clocks}
+    if ab is not None:
+        line["lm_loop_ab"] = ab
     line.update(extras)
     print(json.dumps(line))
     if dist is not None:

@@ -76,9 +76,14 @@ typedef struct liogpu_params {
   float knn_phase1_radius;   /* radius of the cheap first search phase; 0 = auto (2 x map leaf),
                                 < 0 = single phase.  Tuning only: results do not depend on it.   */
   int profile_kernels;       /* 1: time the phases of the LM loop on the device (bench.py)        */
-  int s2m_path;              /* 0 = the whole LM loop as ONE persistent cooperative launch (default);
-                                1 = two launches per iteration (the round-1 path, kept for A/B runs).
-                                Tuning only: results do not depend on it.                          */
+  int s2m_path;              /* how the LM loop of liogpu_scan2map is run.  Tuning only: results do not
+                                depend on it.
+                                0 = automatic (the faster one for the workload as measured on B200:
+                                    currently always 1, see DESIGN.md "A/B of the LM loop");
+                                1 = two launches per Gauss-Newton iteration (search + plane fit; leftovers
+                                    + fixed-order reduction + 6x6 tail), chained with programmatic launch;
+                                2 = the whole loop as ONE persistent cooperative launch with candidate
+                                    sets and the exact no-search certificate (s2m_fused.cuh).           */
   int s2m_no_certificate;    /* 1 = never use the exact no-search certificate (A/B runs): every point
                                 with a candidate set is searched again.  Results do not depend on it. */
   int reserved[3];
@@ -108,7 +113,7 @@ typedef struct liogpu_s2m_info {
   float left_kernel_ms;   /* summed device time of the leftover search + reduction + 6x6 tail
                              (s2m_path 1: of s2m_left_kernel)                                       */
   int main_kernel_launches, left_kernel_launches; /* executed iterations timed                     */
-  /* s2m_path 0 only: */
+  /* s2m_path 2 only: */
   int certified;     /* last iteration: points whose 5 neighbours came from the exact certificate  */
   int leftovers;     /* last iteration: points finished by the warp-cooperative full-gate search   */
   float tail_ms;     /* profile_kernels: summed time between a CTA's partial row and the release of
@@ -336,7 +341,7 @@ int liogpu_surf_optimization(liogpu_ctx* ctx, const void* scan_ds, int n, int st
 /* liogpu_scan2map with the per-point results of its LAST EXECUTED iteration exposed (same outputs and meaning as
  * liogpu_surf_optimization; any pointer may be NULL).  Parity tests use it to check every iteration of the
  * on-device loop — including the ones that take the no-search certificate — against a surfOptimization pass of the
- * reference at the pose that iteration started from (info->pose_hist).  Runs the one-launch loop (s2m_path 0). */
+ * reference at the pose that iteration started from (info->pose_hist).  Runs the one-launch loop (s2m_path 2). */
 int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, float pose_io[6],
                           float matP_io[36], int* degenerate_io, int max_iter, liogpu_s2m_info* info,
                           int* nn_idx, float* nn_d2, float* coeff, unsigned char* flag, unsigned char* tie);

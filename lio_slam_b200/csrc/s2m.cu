@@ -337,6 +337,30 @@ __device__ __forceinline__ int warp_knn5(const float4 q, const GridParams& g, co
 // less than the margin (minus 1 mm for rounding) since then, fewer than five map points can lie within 1 m of
 // it (triangle inequality), and the main kernel skips it without searching.  Exact, not heuristic.
 constexpr float HOPELESS_MARGIN = 0.25f;
+// Generalised (round 2): the leftover search now learns the distance of the 5th-nearest map point even when it lies
+// beyond the gate (up to 1 m + HOPELESS_MARGIN); a point whose 5th neighbour is sqrt(d5) > 1 m away cannot have five
+// neighbours within the gate until it has moved sqrt(d5) - 1 m.  hopeless[i] = (position at search time, that margin
+// minus 1 mm; 0 = no claim).  The old rule is the special case "fewer than five points inside the extended gate".
+constexpr float HOPELESS_REL = 1e-5f;
+
+// Full-gate search of a point the phase-1 gate could not settle, warp-cooperative, in two stages: most such points
+// have their five neighbours within 0.7 m, so a first pass over that ball usually settles them (a quarter of the rows
+// and candidates of the 1.25 m ball); only the rest walk the extended gate.  On return t holds the five nearest map
+// points closer than sqrt(r2) (ascending), r2 = the squared radius that was enumerated completely, and t.rej the
+// best distance among everything else that was visited.
+constexpr float LEFT_STAGE1 = 0.7f;
+__device__ __forceinline__ void leftover_search(const float4 q, const GridParams& g, const float ge2,
+                                                   const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start,
+                                                   const int lane, Top5& t, float& r2) {
+  r2 = LEFT_STAGE1 * LEFT_STAGE1;
+  if (r2 < g.gate_d2) {
+    warp_knn5(q, g, r2, map_sorted, cell_start, lane, t, r2);
+    if (t.d(t.k4) < r2) return;  // five points inside the ball, all of it enumerated: exact
+  }
+  r2 = ge2;
+  warp_knn5(q, g, ge2, map_sorted, cell_start, lane, t, ge2);
+}
+
 
 // ---- the 6x6 tail of LMOptimization (mapOptmization.cpp:1721-1835), executed by ONE WARP ----
 // A single thread walking these 6x6 routines through local memory cost ~90 us per iteration (~170 us on
@@ -891,8 +915,7 @@ s2m_main_kernel(const S2mArgs A) {
         const float4 hr = A.hopeless[i];
         if (hr.w > 0.f) {
           const float dx = sel.x - hr.x, dy = sel.y - hr.y, dz = sel.z - hr.z;
-          const float lim = HOPELESS_MARGIN - 1e-3f;
-          skip = (dx * dx + dy * dy + dz * dz) < lim * lim;  // still cannot have 5 neighbours within the gate
+          skip = (dx * dx + dy * dy + dz * dz) * (1.f + HOPELESS_REL) < hr.w * hr.w;  // still cannot have 5 neighbours within the gate
         }
       }
       if (p0 >= 0) {
@@ -1084,20 +1107,22 @@ s2m_left_kernel(const S2mArgs A) {
       if (mine >= 0) { ori = A.scan[mine]; sel = apply_T(sT, ori); }
       Top5 t;
       t.init(A.g.gate_d2);
-      int my_ext = 0;
+      const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;
       for (int j = 0; j < cnt; ++j) {  // the warp searches for point j; lane j keeps the answer
         float4 q;
         q.x = __shfl_sync(0xffffffffu, sel.x, j); q.y = __shfl_sync(0xffffffffu, sel.y, j);
         q.z = __shfl_sync(0xffffffffu, sel.z, j); q.w = 0.f;
         Top5 tj;
-        const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;
-        const int n_ext = warp_knn5(q, A.g, ge * ge, A.map_sorted, A.cell_start, lane, tj);
-        if (lane == j) { t = tj; my_ext = n_ext; }
+        float r2;
+        leftover_search(q, A.g, ge * ge, A.map_sorted, A.cell_start, lane, tj, r2);
+        if (lane == j) t = tj;
       }
       if (mine >= 0) {
         finish_point(A, mine, ori, sel, t, sTrig, row, rhs, flag, tie);
-        const bool hopeless = !(t.d(t.k4) < A.g.gate_d2) && my_ext < 5;
-        A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, hopeless ? 1.f : 0.f);
+        // d(k4) = the 5th-nearest distance^2 when five points lie inside the enumerated ball, else its radius^2
+        const bool found = t.d(t.k4) < A.g.gate_d2;
+        const float margin = found ? 0.f : sqrtf(t.d(t.k4)) * (1.f - HOPELESS_REL) - sqrtf(A.g.gate_d2) - 1e-3f;
+        A.hopeless[mine] = make_float4(sel.x, sel.y, sel.z, margin > 0.f ? margin : 0.f);
       }
     }
 #pragma unroll
@@ -1363,7 +1388,7 @@ int scan2map_dev(Ctx* c, const float4* scan4, int n, float pose_io[6], float mat
   if (max_iter < 1 || max_iter > LIOGPU_MAX_ITER) { c->err = "max_iter out of range"; return LIOGPU_E_INVALID; }
   // the fused loop keeps its chunk-offset table in shared memory: sweeps beyond 1,048,576 points (none of the
   // reference's sensors) take the two-kernel path
-  if (c->prm.s2m_path == 0 && div_up(n, FZ_THREADS) <= FZ_MAXCHUNKS && fused_grid(c) > 1)
+  if (c->prm.s2m_path == 2 && div_up(n, FZ_THREADS) <= FZ_MAXCHUNKS && fused_grid(c) > 1)
     return scan2map_fused_dev(c, scan4, n, pose_io, matP_io, degenerate_io, max_iter, info, nullptr);
   return scan2map_legacy_dev(c, scan4, n, pose_io, matP_io, degenerate_io, max_iter, info);
 }

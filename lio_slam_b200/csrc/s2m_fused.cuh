@@ -331,24 +331,6 @@ union FzSmem {
   FzLeftSmem l;
 };
 
-// Full-gate search of a point the phase-1 gate could not settle, warp-cooperative, in two stages: most such points
-// have their five neighbours within 0.7 m, so a first pass over that ball usually settles them (a quarter of the rows
-// and candidates of the 1.25 m ball); only the rest walk the extended gate.  On return t holds the five nearest map
-// points closer than sqrt(r2) (ascending), r2 = the squared radius that was enumerated completely, and t.rej the
-// best distance among everything else that was visited.
-constexpr float FZ_LEFT_STAGE1 = 0.7f;
-__device__ __forceinline__ void fz_leftover_search(const float4 q, const GridParams& g, const float ge2,
-                                                   const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start,
-                                                   const int lane, Top5& t, float& r2) {
-  r2 = FZ_LEFT_STAGE1 * FZ_LEFT_STAGE1;
-  if (r2 < g.gate_d2) {
-    warp_knn5(q, g, r2, map_sorted, cell_start, lane, t, r2);
-    if (t.d(t.k4) < r2) return;  // five points inside the ball, all of it enumerated: exact
-  }
-  r2 = ge2;
-  warp_knn5(q, g, ge2, map_sorted, cell_start, lane, t, ge2);
-}
-
 // what a leftover search leaves behind for the next iteration: the candidate set (its five neighbours), the bound
 // (everything else it visited was >= rej away, everything it did not visit is beyond the enumerated radius) and, for
 // a point with fewer than five map points inside the gate, the generalised hopeless marker: its 5th-nearest map
@@ -618,7 +600,7 @@ s2m_fused_kernel(const FusedArgs A) {
             q.x = __shfl_sync(FULL, sel.x, j); q.y = __shfl_sync(FULL, sel.y, j); q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
             Top5 t;
             float r2;
-            fz_leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, t, r2);
+            leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, t, r2);
             if (lane == j) {
               found = t.d(t.k4) < A.g.gate_d2;  // :1641
               fz_store_leftover(A, i, sel, t, r2, found);
@@ -818,7 +800,7 @@ s2m_fused_kernel(const FusedArgs A) {
             q.z = __shfl_sync(FULL, sel.z, j); q.w = 0.f;
             Top5 tj;
             float r2;
-            fz_leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, tj, r2);
+            leftover_search(q, A.g, ge2, A.map_sorted, A.cell_start, lane, tj, r2);
             if (lane == j) { t = tj; my_r2 = r2; }
           }
           if (mine >= 0) {

@@ -2,6 +2,9 @@
 #include "map_optimization_gpu.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -56,10 +59,14 @@ void mapOptimization::extractNearby() {
     for (size_t i = 0; i < times.size(); ++i) times[i] = cloudKeyPoses6D[i].time;
     std::vector<int> ids(2 * cloudKeyPoses3D.size() + 1);
     int n_ids = 0;
+    const auto t_dbg0 = std::chrono::steady_clock::now();
     lastStatus = liogpu_extract_nearby(ctx_, cloudKeyPoses3D.data(), (int)cloudKeyPoses3D.size(), sizeof(PointType), times.data(),
                                        sizeof(double), timeLaserInfoCur, surroundingKeyframeSearchRadius, surroundingKeyframeDensity,
                                        ids.data(), (int)ids.size(), &n_ids);
     ids.resize(lastStatus < 0 ? 0 : n_ids);
+    if (std::getenv("LIORF_DEBUG_TIMING"))
+      std::fprintf(stderr, "[liorf] extract_nearby on device: %d key poses -> %d ids, %.3f ms (device %.3f ms)\n", (int)cloudKeyPoses3D.size(),
+                   n_ids, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_dbg0).count(), (double)liogpu_last_gpu_ms(ctx_));
     surroundingKeyPosesDS = ids;
     extractCloudFromIds(ids);
     return;

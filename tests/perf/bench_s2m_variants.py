@@ -27,7 +27,7 @@ def main():
     import bench
     from lio_slam_b200.liogpu import LioGpu, default_params
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    over = {"fused": {}, "fused_nocert": {"s2m_no_certificate": 1}, "two_kernel": {"s2m_path": 1}}
+    over = {"fused": {"s2m_path": 2}, "fused_nocert": {"s2m_path": 2, "s2m_no_certificate": 1}, "two_kernel": {"s2m_path": 1}}
     for name in args.workloads.split(","):
         w = bench.WORKLOADS[name]
         map4, scans, guesses = bench.make_workload(name, 0, 4)

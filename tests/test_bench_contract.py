@@ -32,8 +32,13 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = run_bench("--workload", "cfg1", "--steps", "5", "--warmup", "3", "--cpu-steps", "1")
-    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    d = run_bench("--workload", "cfg1", "--steps", "5", "--warmup", "3", "--cpu-steps", "3", "--seq-scans", "12")
+    assert BASE_KEYS | {"roofline", "clocks", "cfg1", "cfg4", "cfg5", "lm_loop_ab", "like_for_like"} <= set(d)
+    assert d["cfg4"]["bit_equal_to_1gpu"] is True and d["cfg4"]["n_points"] > 4_000_000
+    assert d["cfg5"]["total_scans"] == 8 * 12 and d["cfg5"]["value"] > 0 and d["cfg5"]["scaling"] == "strong"
+    assert d["cfg5"]["max_position_error_vs_ground_truth_m"] < 0.15
+    assert d["lm_loop_ab"]["fused_one_launch"]["poses_bit_equal_to_two_kernel"] in (True, False)
+    assert set(d["cpu_baseline"]["by_number_of_cores"]) >= {"4"}
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "f32"
     assert d["value"] > 0 and d["gpu_launches"] > 0
     r = d["roofline"]

@@ -1,5 +1,5 @@
-"""The one-launch LM loop (s2m_fused.cuh, params.s2m_path = 0) against the CPU oracle, iteration by iteration, and
-against the two-kernel path of round 1 (s2m_path = 1).  What is specific to it and therefore checked here:
+"""The one-launch LM loop (s2m_fused.cuh, params.s2m_path = 2) against the CPU oracle, iteration by iteration, and
+against the two-kernel path (s2m_path = 1).  What is specific to it and therefore checked here:
   * the exact no-search certificate: every iteration's per-point neighbours / distances / coefficients / flags / tie
     bits must equal a surfOptimization pass of the oracle at the pose that iteration started from, whether the point
     was searched or certified, and the certificate must actually be taken on late iterations;
@@ -45,8 +45,8 @@ def run_all(case, scan, **over):
 def test_fused_equals_two_kernel_path_and_certificate_is_neutral(oracle, small_case, dense_case, which):
     case = dict(small_case, leaf=0.5) if which == "small" else dense_case
     scan = oracle.voxel_grid(case["scan4"], 0.4)[0] if which == "small" else case["scan4"]
-    pose_f, P_f, info_f = run_all(case, scan)
-    pose_n, P_n, info_n = run_all(case, scan, s2m_no_certificate=1)
+    pose_f, P_f, info_f = run_all(case, scan, s2m_path=2)
+    pose_n, P_n, info_n = run_all(case, scan, s2m_path=2, s2m_no_certificate=1)
     pose_l, P_l, info_l = run_all(case, scan, s2m_path=1)
     assert info_f["kernel_launches"] == 1 and info_l["kernel_launches"] > 2
     assert info_f["iterations"] == info_n["iterations"] == info_l["iterations"] >= 3
@@ -70,7 +70,7 @@ def test_fused_equals_two_kernel_path_and_certificate_is_neutral(oracle, small_c
 def test_every_iteration_matches_the_oracle_point_by_point(oracle, small_case, dense_case, which):
     case = dict(small_case, leaf=0.5) if which == "small" else dense_case
     scan = oracle.voxel_grid(case["scan4"], 0.4)[0] if which == "small" else case["scan4"]
-    g = make_ctx(case["leaf"])
+    g = make_ctx(case["leaf"], s2m_path=2)
     try:
         g.set_local_map(case["map4"])
         pose, P, info = g.scan2map(scan, case["guess"])
@@ -104,7 +104,7 @@ def test_fused_sparse_map_far_from_origin(oracle, small_case):
     ds, _ = oracle.voxel_grid(small_case["scan4"], 0.6)
     guess = small_case["guess"].copy(); guess[3:] += off[:3]
     ref_pose, ref_P, ref_info = oracle.scan2map(map4, ds, guess, threads=8)
-    g = make_ctx(0.5)
+    g = make_ctx(0.5, s2m_path=2)
     try:
         g.set_local_map(map4)
         pose, P, info = g.scan2map(ds, guess)
@@ -118,7 +118,19 @@ def test_fused_sparse_map_far_from_origin(oracle, small_case):
 
 def test_fused_is_reproducible_run_to_run(dense_case):
     # dynamic chunk queue, fixed summation order: two runs must agree bit for bit
-    a = run_all(dense_case, dense_case["scan4"])
-    b = run_all(dense_case, dense_case["scan4"])
+    a = run_all(dense_case, dense_case["scan4"], s2m_path=2)
+    b = run_all(dense_case, dense_case["scan4"], s2m_path=2)
     assert np.array_equal(bits(a[0]), bits(b[0]))
     assert np.array_equal(a[2]["JtJ"], b[2]["JtJ"]) and np.array_equal(bits(a[2]["pose_hist"]), bits(b[2]["pose_hist"]))
+
+
+def test_fused_sequence_replay_matches_two_kernel_path(world):
+    # the whole per-scan path (host mirror) with either LM loop: identical iteration counts, poses equal to the last bits
+    import torch
+    from lio_slam_b200 import replay, synth_torch
+    seq = synth_torch.make_sequence(world, 64, 24, seed=9, device=torch.device("cuda", 0), step=0.35)
+    a = replay.replay_sequence(replay.kitti_params(s2m_path=1), seq)
+    b = replay.replay_sequence(replay.kitti_params(s2m_path=2), seq)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.abs(a[0] - b[0]).max() <= 2e-6
+    print("bit-equal poses:", int((a[0].view(np.uint32) == b[0].view(np.uint32)).all(axis=1).sum()), "of 24")
