@@ -443,6 +443,7 @@ def cpu_cfg5_sample(seq, n=40):
     from replay_oracle import replay_sequence_oracle
     o, kind = open_oracle()
     threads = os.cpu_count() or 1
+    n = min(n, len(seq["offs"]) - 1)
     replay_sequence_oracle(o, seq, count=min(6, n), threads=threads)  # warm-up
     poses, iters, nds, st = replay_sequence_oracle(o, seq, count=n, threads=threads)
     return {"value": 1e3 * st["scans"] / st["wall_ms"], "unit": "scans/s", "cores": threads, "kind": "port",
@@ -463,6 +464,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg1 / cfg4 / cfg5 records")
     ap.add_argument("--seq-scans", type=int, default=200, help="sweeps per sequence of the cfg5 record")
     ap.add_argument("--seq-concurrency", type=int, default=0, help="sequences replayed concurrently per rank (0 = all of the rank's)")
+    ap.add_argument("--only", default="", help="development: run only this extra record (cfg4 | cfg5) and print it")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -510,6 +512,17 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.only:
+        if args.only == "cfg4":
+            rec = bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank)
+        else:
+            rec = bench_cfg5(torch, dist, rank, world_size, local_rank, n_scans=args.seq_scans, concurrency=args.seq_concurrency)[0]
+        if rank == 0:
+            print(json.dumps(rec))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # every rank runs the SAME synthetic sweeps (its own copy, its own GPU, no communication): N-GPU work is
     # then exactly N x the 1-GPU work and the scaling number is not blurred by data-dependent iteration counts

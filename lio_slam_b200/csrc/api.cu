@@ -228,6 +228,16 @@ int liogpu_create(liogpu_ctx** out, const liogpu_params* params) {
     liogpu_destroy(ctx);
     return LIOGPU_E_CUDA;
   }
+  {
+    DevBuf* bufs[] = {&c.raw_in, &c.raw_out, &c.scan4, &c.scan_ds4, &c.map_raw4, &c.map4, &c.map_sorted, &c.cell_start,
+                      &c.keys0, &c.keys1, &c.vals0, &c.vals1, &c.counters, &c.scan_tmp, &c.seg_flag, &c.seg_start,
+                      &c.vox_setup, &c.grid_setup, &c.minmax, &c.lm_state, &c.partials, &c.block_counter, &c.misc,
+                      &c.fail_buf, &c.prev_nn, &c.hopeless, &c.fz_rows, &c.fz_left, &c.fz_lb, &c.fz_probe, &c.tile_plan,
+                      &c.tile_hist, &c.tile_pts, &c.tile_out, &c.dbg_idx, &c.dbg_d2, &c.dbg_coeff, &c.dbg_flag, &c.dbg_tie,
+                      &c.imu_tab, &c.dsk_flags, &c.dsk_scan, &c.lm_flag, &c.lm_pos, &c.lm_a, &c.lm_b, &c.lm_md, &c.lm_left,
+                      &c.lm_out, &c.lm_stats, &c.sor_setup, &c.sor_sorted, &c.sor_cell_start, &c.kf_tab};
+    for (DevBuf* b : bufs) { b->stream = c.stream; b->async = true; }
+  }
   // scratch hint of allocateMemory (mapOptmization.cpp:333-335)
   const size_t hint = (size_t)params->n_scan * (size_t)(params->horizon_scan > 0 ? params->horizon_scan : 1);
   c.scan4.reserve(hint * sizeof(float4));
@@ -255,6 +265,7 @@ void liogpu_destroy(liogpu_ctx* ctx) {
                     &c.sor_sorted, &c.sor_cell_start};
   for (DevBuf* b : bufs) b->release();
   for (auto& kv : c.keyframes) kv.second.first.release();
+  for (void* slab : c.kf_slabs) cudaFree(slab);
   if (c.h_pinned) cudaFreeHost(c.h_pinned);
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
@@ -397,15 +408,38 @@ int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int st
   // the old one only on success: a failed overwrite keeps the previous keyframe and nothing leaks
   const bool special = xyzi == LIOGPU_DEVICE_RESIDENT || xyzi == LIOGPU_UPLOADED_SCAN;
   if (!special && (n < 0 || (n > 0 && !xyzi) || !stride_ok(stride))) { c->err = "liogpu_keyframe_put: bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
+  int n_in = n;
+  if (xyzi == LIOGPU_DEVICE_RESIDENT) { if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; } n_in = c->resident_n; }
+  if (xyzi == LIOGPU_UPLOADED_SCAN) { if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; } n_in = c->upload[c->upload_ready].n; }
   DevBuf fresh;
+  {
+    auto old = c->keyframes.find(id);
+    const size_t need = ((size_t)(n_in > 0 ? n_in : 1) * sizeof(float4) + 255) & ~(size_t)255;
+    if (old != c->keyframes.end() && old->second.first.cap >= need) {
+      fresh = old->second.first;  // overwrite in place (same id, fits): nothing can fail between here and the copy
+    } else {
+      constexpr size_t SLAB = 32u << 20;
+      if (c->kf_slabs.empty() || c->kf_slab_used + need > c->kf_slab_size) {
+        const size_t sz = need > SLAB ? need : SLAB;
+        void* slab = nullptr;
+        LIOGPU_CUDA_OK(c, cudaMalloc(&slab, sz));
+        c->kf_slabs.push_back(slab);
+        c->kf_slab_used = 0;
+        c->kf_slab_size = sz;
+      }
+      fresh.p = (char*)c->kf_slabs.back() + c->kf_slab_used;
+      fresh.cap = need;
+      fresh.pooled = true;
+      c->kf_slab_used += need;  // an overwritten, smaller keyframe's bytes stay in their slab until liogpu_keyframe_clear
+    }
+  }
   rc = load_cloud(c, xyzi, n, stride, fresh);
   if (rc == LIOGPU_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {  // raw_in staging is reused by the next call
     c->err = std::string("liogpu_keyframe_put: ") + cudaGetErrorString(cudaGetLastError());
     rc = LIOGPU_E_CUDA;
   }
-  if (rc) { fresh.release(); return rc; }
+  if (rc) return rc;
   auto& slot = c->keyframes[id];
-  slot.first.release();
   slot.first = fresh;
   slot.second = n;
   return LIOGPU_OK;
@@ -419,6 +453,9 @@ int liogpu_keyframe_clear(liogpu_ctx* ctx) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->keyframes) kv.second.first.release();
   c->keyframes.clear();
+  for (void* slab : c->kf_slabs) cudaFree(slab);
+  c->kf_slabs.clear();
+  c->kf_slab_used = c->kf_slab_size = 0;
   return LIOGPU_OK;
 }
 

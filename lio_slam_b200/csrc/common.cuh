@@ -13,24 +13,32 @@
 namespace liogpu {
 
 // ---- device buffer that grows on demand (steady state: no allocation on the per-scan path) ----
+// Context buffers are allocated STREAM-ORDERED on the context's stream (cudaMallocAsync / cudaFreeAsync): growing one
+// never synchronises the device, so several contexts sharing a GPU (batch offline mapping, one sequence per context)
+// do not stall each other while their buffers find their size.
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  cudaStream_t stream = nullptr;
+  bool async = false;   // stream-ordered allocation on `stream`
+  bool pooled = false;  // carved out of a slab (keyframe pool): never freed individually
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    size_t want = bytes + bytes / 4 + 256;
+    if (pooled) return cudaErrorMemoryAllocation;
+    size_t want = bytes + bytes / 2 + 4096;
     void* np_ = nullptr;
-    cudaError_t e = cudaMalloc(&np_, want);
+    cudaError_t e = async ? cudaMallocAsync(&np_, want, stream) : cudaMalloc(&np_, want);
     if (e != cudaSuccess) return e;
-    if (p) cudaFree(p);
+    if (p) { if (async) cudaFreeAsync(p, stream); else cudaFree(p); }
     p = np_;
     cap = want;
     return cudaSuccess;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !pooled) { if (async) cudaFreeAsync(p, stream); else cudaFree(p); }
     p = nullptr;
     cap = 0;
+    pooled = false;
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -136,8 +144,11 @@ struct Ctx {
   DevBuf dbg_idx, dbg_d2, dbg_coeff, dbg_flag, dbg_tie;
   // pinned host mirrors
   void* h_pinned = nullptr;  // 128 KiB: small readbacks in the first 64 KiB, IMU table in the second
-  // keyframes (lidar frame, packed float4)
+  // keyframes (lidar frame, packed float4), carved out of 32 MiB slabs: surfCloudKeyFrames.push_back (MO:2142) costs
+  // no cudaMalloc (which would synchronise the whole device, i.e. every other context on it)
   std::map<int, std::pair<DevBuf, int>> keyframes;
+  std::vector<void*> kf_slabs;
+  size_t kf_slab_used = 0, kf_slab_size = 0;
   // deskew
   DevBuf imu_tab, dsk_flags, dsk_scan;
   // publishLocalMap (localmap.cu): crop / outlier-filter scratch and the filter's own neighbour grid
