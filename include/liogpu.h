@@ -356,7 +356,8 @@ int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int strid
 
 /* Copy out the cloud produced by the call RIGHT BEFORE this one (liogpu_build_local_map, liogpu_merge_keyframes,
  * liogpu_publish_local_map, liogpu_voxel_tile) without recomputing it: a caller that does not know the size passes
- * cap_out = 0 to the producing call, reads the size from its LIOGPU_E_CAPACITY return, sizes its buffer and fetches. */
+ * cap_out = 0 to the producing call, reads the size from its LIOGPU_E_CAPACITY return, sizes its buffer and fetches.
+ * Returns the status the producing call would have returned (LIOGPU_OK or LIOGPU_W_LEAF_OVERFLOW). */
 int liogpu_fetch_result(liogpu_ctx* ctx, void* xyzi_out, int out_stride, int cap_out, int* n_out);
 
 /* Timing hook for bench.py: device milliseconds of the last call's kernels (events on ctx's stream). */

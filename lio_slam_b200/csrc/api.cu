@@ -488,7 +488,7 @@ int liogpu_build_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_map = m;
-  c->last_result = c->map4.as<float4>(); c->last_result_n = m;
+  c->last_result = c->map4.as<float4>(); c->last_result_n = m; c->last_result_status = overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
   if (xyzi_out) {
     if (m > cap_out) { c->err = "liogpu_build_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->map4.as<float4>(), m, xyzi_out, out_stride);
@@ -529,7 +529,7 @@ int liogpu_voxel_tile(liogpu_ctx* ctx, const int* ids, const float* pose6s, int 
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
-  c->last_result = c->tile_out.as<float4>(); c->last_result_n = m;
+  c->last_result = c->tile_out.as<float4>(); c->last_result_n = m; c->last_result_status = overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_voxel_tile: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, c->tile_out.as<float4>(), m, xyzi_out, out_stride);
@@ -612,7 +612,7 @@ int liogpu_publish_local_map(liogpu_ctx* ctx, const int* ids, const float* pose6
   if (rc) return rc;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
-  c->last_result = result; c->last_result_n = m;
+  c->last_result = result; c->last_result_n = m; c->last_result_status = info->leaf_overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_publish_local_map: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, result, m, xyzi_out, out_stride);
@@ -651,7 +651,7 @@ int liogpu_merge_keyframes(liogpu_ctx* ctx, const int* ids, const float* pose6s,
   }
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
   *n_out = m;
-  c->last_result = result; c->last_result_n = m;
+  c->last_result = result; c->last_result_n = m; c->last_result_status = overflow ? LIOGPU_W_LEAF_OVERFLOW : LIOGPU_OK;
   if (xyzi_out && m > 0) {
     if (m > cap_out) { c->err = "liogpu_merge_keyframes: output capacity too small"; return LIOGPU_E_CAPACITY; }
     rc = store_cloud(c, result, m, xyzi_out, out_stride);
@@ -905,7 +905,8 @@ int liogpu_fetch_result(liogpu_ctx* ctx, void* xyzi_out, int out_stride, int cap
   if (!c->last_result) { c->err = "liogpu_fetch_result: no result pending (it serves only the call right before it)"; return LIOGPU_E_INVALID; }
   *n_out = c->last_result_n;
   if (c->last_result_n > cap_out) { c->err = "liogpu_fetch_result: output capacity too small"; return LIOGPU_E_CAPACITY; }
-  return store_cloud(c, c->last_result, c->last_result_n, xyzi_out, out_stride);
+  const int rc = store_cloud(c, c->last_result, c->last_result_n, xyzi_out, out_stride);
+  return rc ? rc : c->last_result_status;  // the producing call's warning travels with its result
 }
 
 int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int stride) {

@@ -104,7 +104,7 @@ struct LmDevState {
   int certified;      // last executed iteration: points whose five neighbours came from the certificate (no grid walk)
   int leftovers;      // last executed iteration: points finished by the warp-cooperative full-gate search
   int cert_hist[LIOGPU_MAX_ITER], left_hist[LIOGPU_MAX_ITER], seed_hist[LIOGPU_MAX_ITER];
-  int pad_[1];
+  int main_finalized_iter;  // two-kernel path: value of `iter` after the main kernel's last block ran the tail itself
 };
 
 // host-visible context
@@ -163,6 +163,7 @@ struct Ctx {
   // result of the last build_local_map / merge_keyframes / publish_local_map / voxel_tile, for liogpu_fetch_result
   const float4* last_result = nullptr;
   int last_result_n = 0;
+  int last_result_status = 0;  // the warning the producing call would have returned (LIOGPU_W_LEAF_OVERFLOW)
   // liogpu_upload_scan_async: two staging slots filled on a copy stream
   cudaStream_t copy_stream = nullptr;
   struct Upload { DevBuf raw; cudaEvent_t ev = nullptr; int n = 0, stride = 0; bool valid = false; } upload[2];

@@ -318,7 +318,6 @@ void mapOptimization::publishLocalMap() {  // :2442-2541; the reference calls it
   if (st == LIOGPU_E_CAPACITY) {  // the cloud grew: fetch it, the pipeline is not run twice
     localMapCloud.resize(n);
     st = liogpu_fetch_result(ctx_, localMapCloud.data(), sizeof(PointType), n, &n);
-    if (st == LIOGPU_OK && lastLocalMapInfo.leaf_overflow) st = LIOGPU_W_LEAF_OVERFLOW;
   }
   lastStatus = st;
   localMapCloud.resize(st < 0 ? 0 : n);

@@ -332,7 +332,7 @@ class LioGpu:
             st = self._check(self.lib.liogpu_voxel_tile(self.h, ids.ctypes.data, poses.ctypes.data, ids.shape[0], C.c_float(leaf),
                                                         tile, n_tiles, None, 16, 0, C.byref(n_out), C.byref(info)))
             host = np.empty((max(n_out.value, 1), 4), np.float32)
-            self._check(self.lib.liogpu_fetch_result(self.h, host.ctypes.data, 16, host.shape[0], C.byref(n_out)))
+            st = self._check(self.lib.liogpu_fetch_result(self.h, host.ctypes.data, 16, host.shape[0], C.byref(n_out)))
             res = host[: n_out.value].copy()
         else:
             ptr, cap = out
@@ -358,8 +358,6 @@ class LioGpu:
         if st == E_CAPACITY:  # the cloud exists on the device: copy it out without recomputing
             out = np.empty((n_out.value, 4), np.float32)
             st = self.lib.liogpu_fetch_result(self.h, out.ctypes.data, 16, out.shape[0], C.byref(n_out))
-            if st == OK and info.leaf_overflow:
-                st = W_LEAF_OVERFLOW
         self._check(st)
         d = {k: getattr(info, k) for k, _ in LocalMapInfo._fields_ if k != "reserved"}
         return out[: n_out.value].copy(), d, st
