@@ -875,8 +875,11 @@ __device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, cons
 // usual case from the second iteration on — the last block to finish also adds the partial rows in a fixed order and
 // runs the 6x6 tail, and the iteration's second launch returns at once (st->main_finalized_iter).  Iteration 0 of a
 // dense map (thousands of leftovers, clustered) and sparse maps still take the two-launch route.
+// LATE = false is the lean kernel of iterations 0 and 1 (thousands of leftovers there: everything is deferred, exactly
+// the round-1 kernel); LATE = true is launched from iteration 2 on, where leftovers are rare.
 constexpr int MAIN_INPLACE = 16;
 
+template <bool LATE>
 __global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
 s2m_main_kernel(const S2mArgs A) {
   __shared__ float sT[12];
@@ -966,7 +969,8 @@ s2m_main_kernel(const S2mArgs A) {
     } else {
       need2 = true;
     }
-    keep_ori = ori; keep_sel = sel; keep_t = t;
+    if (LATE) { keep_ori = ori; keep_sel = sel; keep_t = t; }
+    else if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
   }
   // leftover indices, in thread order
   const unsigned fm = __ballot_sync(0xffffffffu, need2);
@@ -980,7 +984,7 @@ s2m_main_kernel(const S2mArgs A) {
 #pragma unroll
   for (int w = 0; w < S2M_THREADS / 32; ++w) { if (w < warp) fbase += s_wfail[w]; nfail += s_wfail[w]; }
   const int frank = fbase + __popc(fm & ((1u << lane) - 1u));
-  const bool inplace = nfail > 0 && nfail <= MAIN_INPLACE;
+  const bool inplace = LATE && nfail > 0 && nfail <= MAIN_INPLACE;
   if (inplace) {
     // a handful: the block's warps finish them here, one warp-cooperative full-gate search each
     if (need2) s_lslot[frank] = (unsigned char)tid;
@@ -1010,7 +1014,7 @@ s2m_main_kernel(const S2mArgs A) {
   } else if (need2) {
     A.fail_seg[(size_t)blockIdx.x * S2M_THREADS + frank] = i;
   }
-  if (i < A.nq && !need2) finish_point(A, i, keep_ori, keep_sel, keep_t, sTrig, row, rhs, flag, tie);
+  if (LATE && i < A.nq && !need2) finish_point(A, i, keep_ori, keep_sel, keep_t, sTrig, row, rhs, flag, tie);
 #pragma unroll
   for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
   rows[tid][6] = rhs;
@@ -1078,7 +1082,7 @@ s2m_main_kernel(const S2mArgs A) {
   }
   __syncthreads();
   if (A.mode != 0) return;
-  if (s_carry != 0) {  // something was deferred: s2m_left_kernel finishes the iteration
+  if (!LATE || s_carry != 0) {  // something was deferred: s2m_left_kernel finishes the iteration
     if (tid == 0) A.st->main_finalized_iter = -1;
     return;
   }
@@ -1554,7 +1558,10 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
     for (int it = 0; it < todo; ++it) {
       const bool first = launched + it == 0;
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
-      if (two_phase || !first) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
+      if (two_phase || !first) {
+        if (launched + it >= 2) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel<true>, main_blocks, S2M_THREADS, c->stream, A));
+        else LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel<false>, main_blocks, S2M_THREADS, c->stream, A));
+      }
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
       LIOGPU_CUDA_OK(c, launch_pdl(s2m_left_kernel, left_blocks, LEFT_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 2], c->stream));
@@ -1632,7 +1639,7 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
                        c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
   A.mode = 1;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<false><<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
   s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
   c->launches += 2;
   LIOGPU_CUDA_OK(c, cudaGetLastError());

@@ -5,7 +5,10 @@ the data path: every rank works on its own points and results are concatenated i
 * full-map VoxelGrid rebuild (configs[3]): points are split into contiguous ranges of the voxel index
   (iz, iy) — spatial slabs/tiles in PCL's output order — by a STABLE partition, each rank voxelises its
   range, and the rank outputs concatenated in rank order reproduce the single-GPU output bit for bit,
-  because a voxel never spans two ranges and the within-voxel summation order is preserved.
+  because a voxel never spans two ranges and the within-voxel summation order is preserved.  The product
+  makes this plan ON THE DEVICE (liogpu_voxel_tile, csrc/tile.cu); `plan_voxel_tiles` restates the same plan
+  with numpy so that the CPU suite (oracle workers, gloo world_size 2) exercises the N > 1 logic and a GPU test
+  can hold the device plan against it.
 """
 from __future__ import annotations
 
@@ -28,26 +31,43 @@ def voxel_guard_fires(cloud4: np.ndarray, leaf: float) -> bool:
     return int(d[0]) * int(d[1]) * int(d[2]) > np.iinfo(np.int32).max
 
 
-def plan_voxel_tiles(cloud4: np.ndarray, leaf: float, n_tiles: int):
-    """Split the cloud into n_tiles contiguous ranges of the (iz, iy) voxel row index, balanced by point count.
+TILE_MAX_BINS = 65536
 
-    Returns (tile_of_point int32[n], bounds): tile t holds the voxel rows with key in [bounds[t], bounds[t+1]).
+
+def plan_voxel_tiles(cloud4: np.ndarray, leaf: float, n_tiles: int):
+    """Host restatement of the DEVICE-side tile plan of liogpu_voxel_tile (csrc/tile.cu), for the CPU tests of the
+    N > 1 path (the product plans on the GPU; nothing here is on a measured path): coarse histogram of the voxel-row
+    index (iz, iy) — at most 65,536 bins — and tile t = the bins between the first bin whose cumulative count reaches
+    t*n/N and the one that reaches (t+1)*n/N: contiguous ranges of voxel rows balanced by point count.
+
+    Returns (tile_of_point int32[n], bounds): tile t holds the bins [bounds[t], bounds[t+1]).
     Non-finite points are dropped by VoxelGrid anyway; they are sent to tile 0."""
     inv = np.float32(1.0) / np.float32(leaf)
     finite = np.isfinite(cloud4[:, :3]).all(axis=1)
-    iy = np.floor(cloud4[:, 1].astype(np.float32) * inv).astype(np.int64)
-    iz = np.floor(cloud4[:, 2].astype(np.float32) * inv).astype(np.int64)
+    n_valid = int(finite.sum())
+    if n_valid == 0:
+        return np.zeros(cloud4.shape[0], np.int32), [0] * n_tiles + [1]
+    y = cloud4[:, 1].astype(np.float32); z = cloud4[:, 2].astype(np.float32)
+    iy = np.floor(y * inv).astype(np.int64); iz = np.floor(z * inv).astype(np.int64)
     iy[~finite] = 0; iz[~finite] = 0
-    iy0, iz0 = iy[finite].min(initial=0), iz[finite].min(initial=0)
-    dy = int(iy[finite].max(initial=0) - iy0 + 1)
-    key = (iz - iz0) * dy + (iy - iy0)
-    order = np.sort(key[finite])
-    bounds = [int(order[0]) if order.size else 0]
+    iy0 = int(np.floor(y[finite].min() * inv)); iz0 = int(np.floor(z[finite].min() * inv))
+    dy = int(np.floor(y[finite].max() * inv)) - iy0 + 1
+    dz = int(np.floor(z[finite].max() * inv)) - iz0 + 1
+    nrows = dy * dz
+    shift = 0
+    while (((nrows - 1) >> shift) + 1) > TILE_MAX_BINS:
+        shift += 1
+    nbins = ((nrows - 1) >> shift) + 1
+    bins = ((iz - iz0) * dy + (iy - iy0)) >> shift
+    hist = np.bincount(bins[finite], minlength=nbins)
+    cum = np.concatenate([[0], np.cumsum(hist)])[:-1]          # exclusive prefix
+    bounds = [0]
     for t in range(1, n_tiles):
-        q = order[min(order.size - 1, (order.size * t) // n_tiles)] if order.size else 0
-        bounds.append(max(int(q), bounds[-1]))
-    bounds.append(int(order[-1]) + 1 if order.size else 1)
-    tile = np.searchsorted(np.array(bounds[1:-1], dtype=np.int64), key, side="right").astype(np.int32)
+        want = (n_valid * t) // n_tiles
+        b = int(np.searchsorted(cum, want, side="left"))       # first bin with cum[bin] >= want
+        bounds.append(max(min(b, nbins), bounds[-1]))
+    bounds.append(nbins)
+    tile = (np.searchsorted(np.array(bounds[1:-1], dtype=np.int64), bins, side="right")).astype(np.int32)
     tile[~finite] = 0
     return tile, bounds
 

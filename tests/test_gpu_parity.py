@@ -364,10 +364,15 @@ def test_device_planned_tiles_equal_build_local_map(gpu, oracle, world, tiles):
     ids = np.arange(8)
     single, st = gpu.build_local_map(ids, poses, 0.5, fetch=True, cap=want.shape[0])
     assert_biteq(single, want, "single GPU")
+    from lio_slam_b200 import sharding
+    raw = np.concatenate([oracle.transform_cloud(c, p) for c, p in zip(clouds, poses)])
+    host_tile, host_bounds = sharding.plan_voxel_tiles(raw, 0.5, tiles)   # numpy restatement of the device plan
     parts, npts = [], 0
     for t in range(tiles):
         out, info, st = gpu.voxel_tile(ids, poses, 0.5, t, tiles)
         assert st == 0 and info["n_points"] == sum(c.shape[0] for c in clouds)
+        assert (info["bin_lo"], info["bin_hi"]) == (host_bounds[t], host_bounds[t + 1]), "device plan != host restatement"
+        assert info["n_tile_points"] == int((host_tile == t).sum())
         npts += info["n_tile_points"]
         parts.append(out)
     assert npts == sum(c.shape[0] for c in clouds)                    # every point belongs to exactly one tile
