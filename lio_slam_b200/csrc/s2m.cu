@@ -353,7 +353,7 @@ __device__ __forceinline__ void leftover_search(const float4 q, const GridParams
                                                    const float4* __restrict__ map_sorted, const uint32_t* __restrict__ cell_start,
                                                    const int lane, Top5& t, float& r2) {
   r2 = LEFT_STAGE1 * LEFT_STAGE1;
-  if (r2 < g.gate_d2) {
+  if (r2 < g.gate_d2 && g.gate1_d2 < g.gate_d2) {  // dense map only: on a sparse one the five are usually farther (measured)
     warp_knn5(q, g, r2, map_sorted, cell_start, lane, t, r2);
     if (t.d(t.k4) < r2) return;  // five points inside the ball, all of it enumerated: exact
   }
@@ -870,16 +870,6 @@ __device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, cons
   }
 }
 
-// A block whose phase-1 search leaves at most MAIN_INPLACE points unsettled finishes them itself (one warp-cooperative
-// full-gate search per warp and round) instead of handing them to s2m_left_kernel; when NO block defers anything — the
-// usual case from the second iteration on — the last block to finish also adds the partial rows in a fixed order and
-// runs the 6x6 tail, and the iteration's second launch returns at once (st->main_finalized_iter).  Iteration 0 of a
-// dense map (thousands of leftovers, clustered) and sparse maps still take the two-launch route.
-// LATE = false is the lean kernel of iterations 0 and 1 (thousands of leftovers there: everything is deferred, exactly
-// the round-1 kernel); LATE = true is launched from iteration 2 on, where leftovers are rare.
-constexpr int MAIN_INPLACE = 16;
-
-template <bool LATE>
 __global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
 s2m_main_kernel(const S2mArgs A) {
   __shared__ float sT[12];
@@ -888,11 +878,6 @@ s2m_main_kernel(const S2mArgs A) {
   __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
   __shared__ int s_ties, s_wfail[S2M_THREADS / 32], s_iter, s_seeded;
   __shared__ bool s_last;
-  // leftovers finished inside the block (round 2): slots, and the searches' answers handed back to their owners
-  __shared__ unsigned char s_lslot[MAIN_INPLACE];
-  __shared__ u64 s_lkey[MAIN_INPLACE][5];
-  __shared__ float s_lrej[MAIN_INPLACE], s_lr2[MAIN_INPLACE];
-  __shared__ FinSmem s_fin;
 
   __shared__ int s_done0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -915,9 +900,6 @@ s2m_main_kernel(const S2mArgs A) {
   float rhs = 0.f;
   bool flag = false, tie = false, need2 = false;
   int seeded = 0;
-  float4 keep_ori = make_float4(0.f, 0.f, 0.f, 0.f), keep_sel = keep_ori;
-  Top5 keep_t;
-  keep_t.init(A.g.gate_d2);
   if (i < A.nq) {
     const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
@@ -969,58 +951,26 @@ s2m_main_kernel(const S2mArgs A) {
     } else {
       need2 = true;
     }
-    if (LATE) { keep_ori = ori; keep_sel = sel; keep_t = t; }
-    else if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
+    if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
   }
-  // leftover indices, in thread order
+  // leftover indices, in thread order, into this block's segment
   const unsigned fm = __ballot_sync(0xffffffffu, need2);
   if (lane == 0) s_wfail[warp] = __popc(fm);
-  {
-    const int ws = __popc(__ballot_sync(0xffffffffu, seeded != 0));
-    if (lane == 0 && ws) atomicAdd(&s_seeded, ws);
-  }
-  __syncthreads();
-  int nfail = 0, fbase = 0;
-#pragma unroll
-  for (int w = 0; w < S2M_THREADS / 32; ++w) { if (w < warp) fbase += s_wfail[w]; nfail += s_wfail[w]; }
-  const int frank = fbase + __popc(fm & ((1u << lane) - 1u));
-  const bool inplace = LATE && nfail > 0 && nfail <= MAIN_INPLACE;
-  if (inplace) {
-    // a handful: the block's warps finish them here, one warp-cooperative full-gate search each
-    if (need2) s_lslot[frank] = (unsigned char)tid;
-    __syncthreads();
-    const float ge = sqrtf(A.g.gate_d2) + HOPELESS_MARGIN;
-    for (int e = warp; e < nfail; e += S2M_THREADS / 32) {
-      const int slot = s_lslot[e];
-      const int qi = blockIdx.x * S2M_THREADS + slot;
-      const float4 q = apply_T(sT, A.scan[qi]);
-      Top5 tl;
-      float r2;
-      leftover_search(q, A.g, ge * ge, A.map_sorted, A.cell_start, lane, tl, r2);
-      if (lane == 0) {
-        s_lkey[e][0] = tl.k0; s_lkey[e][1] = tl.k1; s_lkey[e][2] = tl.k2; s_lkey[e][3] = tl.k3; s_lkey[e][4] = tl.k4;
-        s_lrej[e] = tl.rej; s_lr2[e] = r2;
-      }
-    }
-    __syncthreads();
-    if (need2) {
-      keep_t.k0 = s_lkey[frank][0]; keep_t.k1 = s_lkey[frank][1]; keep_t.k2 = s_lkey[frank][2];
-      keep_t.k3 = s_lkey[frank][3]; keep_t.k4 = s_lkey[frank][4]; keep_t.rej = s_lrej[frank];
-      const bool found = keep_t.d(keep_t.k4) < A.g.gate_d2;
-      const float margin = found ? 0.f : sqrtf(keep_t.d(keep_t.k4)) * (1.f - HOPELESS_REL) - sqrtf(A.g.gate_d2) - 1e-3f;
-      A.hopeless[i] = make_float4(keep_sel.x, keep_sel.y, keep_sel.z, margin > 0.f ? margin : 0.f);
-      need2 = false;
-    }
-  } else if (need2) {
-    A.fail_seg[(size_t)blockIdx.x * S2M_THREADS + frank] = i;
-  }
-  if (LATE && i < A.nq && !need2) finish_point(A, i, keep_ori, keep_sel, keep_t, sTrig, row, rhs, flag, tie);
 #pragma unroll
   for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
   rows[tid][6] = rhs;
   rows[tid][7] = flag ? 1.f : 0.f;
   if (flag && tie) atomicAdd(&s_ties, 1);
+  {
+    const int ws = __popc(__ballot_sync(0xffffffffu, seeded != 0));
+    if (lane == 0 && ws) atomicAdd(&s_seeded, ws);
+  }
   __syncthreads();
+  if (need2) {
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wfail[w];
+    A.fail_seg[(size_t)blockIdx.x * S2M_THREADS + base + __popc(fm & ((1u << lane) - 1u))] = i;
+  }
   // 27 FP64 sums + count: thread (slice, p) adds its 32 rows' product p; products of two floats are
   // exact in double, so only the order of additions differs from cv::gemm's.
   {
@@ -1045,7 +995,11 @@ s2m_main_kernel(const S2mArgs A) {
     if (tid == 29) sum = (double)s_seeded;
     A.partials_main[(size_t)blockIdx.x * S2M_SUMS + tid] = sum;
   }
-  if (tid == 0) A.block_nfail[blockIdx.x] = inplace ? 0 : nfail;
+  if (tid == 0) {
+    int nf = 0;
+    for (int w = 0; w < S2M_THREADS / 32; ++w) nf += s_wfail[w];
+    A.block_nfail[blockIdx.x] = nf;
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
@@ -1080,54 +1034,6 @@ s2m_main_kernel(const S2mArgs A) {
     *A.fail_total = s_carry;
     *A.ticket = 0u;
   }
-  __syncthreads();
-  if (A.mode != 0) return;
-  if (!LATE || s_carry != 0) {  // something was deferred: s2m_left_kernel finishes the iteration
-    if (tid == 0) A.st->main_finalized_iter = -1;
-    return;
-  }
-  // ---- nothing was deferred: this block adds the partial rows in a fixed order and runs the 6x6 tail ----
-  {
-    constexpr int W = S2M_THREADS / 32, U = 16;
-    double a[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k) a[k] = 0.0;
-    const int nrows = (int)gridDim.x;
-    int b = warp;
-    for (; b + (U - 1) * W < nrows; b += U * W) {
-      double v[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = __ldcg(A.partials_main + (size_t)(b + k * W) * S2M_SUMS + lane);
-#pragma unroll
-      for (int k = 0; k < U; ++k) a[k] += v[k];
-    }
-    {
-      double v[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = (b + k * W < nrows) ? __ldcg(A.partials_main + (size_t)(b + k * W) * S2M_SUMS + lane) : 0.0;
-#pragma unroll
-      for (int k = 0; k < U; ++k) a[k] += v[k];
-    }
-#pragma unroll
-    for (int o = U / 2; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < o; ++k) a[k] += a[k + o];
-    }
-    red[warp][lane] = a[0];
-  }
-  __syncthreads();
-  if (tid < S2M_SUMS) {
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < S2M_THREADS / 32; ++k) sum += red[k][tid];
-    red[0][tid] = sum;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    lm_finalize_warp(A.st, red[0], s_fin, tid);
-    __syncwarp();
-    if (tid == 0) { __threadfence(); A.st->main_finalized_iter = A.st->iter; }  // iter was advanced by the tail
-  }
 }
 
 constexpr int LEFT_THREADS = 256;
@@ -1151,12 +1057,7 @@ s2m_left_kernel(const S2mArgs A) {
     sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
     s_ties = 0;
   }
-  if (tid == 64) {
-    s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = *A.fail_total;
-    // the main kernel's last block already reduced and ran the tail for this iteration (nothing was deferred)
-    // (the marker is rewritten by every executed main launch: the new `iter` when it ran the tail, -1 when it deferred)
-    if (A.mode == 0 && A.st->main_finalized_iter == s_iter0 && s_iter0 > 0) s_done0 = 1;
-  }
+  if (tid == 64) { s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = *A.fail_total; }
   // the offsets of the per-block leftover segments, staged once: the binary search below then runs on
   // shared memory instead of ten dependent L2 round trips
   constexpr int OFF_CAP = 4096;
@@ -1558,10 +1459,7 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
     for (int it = 0; it < todo; ++it) {
       const bool first = launched + it == 0;
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
-      if (two_phase || !first) {
-        if (launched + it >= 2) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel<true>, main_blocks, S2M_THREADS, c->stream, A));
-        else LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel<false>, main_blocks, S2M_THREADS, c->stream, A));
-      }
+      if (two_phase || !first) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
       LIOGPU_CUDA_OK(c, launch_pdl(s2m_left_kernel, left_blocks, LEFT_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 2], c->stream));
@@ -1639,7 +1537,7 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
                        c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
   A.mode = 1;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<false><<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
   s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
   c->launches += 2;
   LIOGPU_CUDA_OK(c, cudaGetLastError());

@@ -375,3 +375,95 @@ def test_voxel_small_cloud_path_matches_pipeline(gpu, oracle, n):
     allbad = np.full((min(n, 50), 4), np.nan, np.float32)
     got, st = gpu.voxel_downsample(allbad, 2.0)
     assert got.shape[0] == 0
+
+
+# ---------------------------------------------------------------- round 2: ABI additions and advisor findings
+def test_upload_scan_async_equals_direct_call(small_case, oracle):
+    """liogpu_upload_scan_async + LIOGPU_UPLOADED_SCAN: same registration as handing the host buffer to the call itself"""
+    from lio_slam_b200.liogpu import LioGpu, UPLOADED, LioGpuError
+    g = LioGpu()
+    try:
+        g.set_local_map(small_case["map4"])
+        ds, _ = oracle.voxel_grid(small_case["scan4"], 0.4)
+        rec = synth.from_packed(ds)                      # 32-byte PointXYZI records
+        want_pose, _, want = g.scan2map(rec, small_case["guess"])
+        with pytest.raises(LioGpuError):                 # nothing uploaded yet
+            g.scan2map(UPLOADED, small_case["guess"])
+        g.upload_scan_async(rec)
+        got_pose, _, got = g.scan2map(UPLOADED, small_case["guess"])
+        assert got["iterations"] == want["iterations"] and np.array_equal(got_pose.view(np.uint32), want_pose.view(np.uint32))
+        # two sweeps in flight, consumed... the newest upload is the one a consumer sees; packed stride works too
+        g.upload_scan_async(ds)
+        n_ds, st = g.voxel_downsample(UPLOADED, 0.8, keep_on_device=True)
+        ref, _ = oracle.voxel_grid(ds, 0.8)
+        assert n_ds == ref.shape[0]
+    finally:
+        g.close()
+
+
+def test_merge_more_keyframes_than_the_old_pose_table_held(oracle):
+    """saveMapService merges EVERY keyframe (mapOptmization.cpp:936-941); round 1 capped a call at 1365"""
+    from lio_slam_b200.liogpu import LioGpu
+    rng = np.random.default_rng(3)
+    k = 1500
+    clouds = [rng.normal(0, 5, (7 + (i % 5), 4)).astype(np.float32) for i in range(k)]
+    poses = np.column_stack([rng.uniform(-0.1, 0.1, (k, 2)), rng.uniform(-3, 3, k), rng.uniform(-200, 200, (k, 2)),
+                             rng.uniform(-2, 2, k)]).astype(np.float32)
+    g = LioGpu()
+    try:
+        for i, c in enumerate(clouds):
+            g.keyframe_put(i, c)
+        got, st = g.merge_keyframes(np.arange(k), poses, 0.0)
+        want = np.concatenate([oracle.transform_cloud(c, p) for c, p in zip(clouds, poses)])
+        assert st == 0 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        got2, st2 = g.merge_keyframes(np.arange(k), poses, 2.0)
+        want2, _ = oracle.voxel_grid(want, 2.0)
+        assert np.array_equal(got2.view(np.uint32), want2.view(np.uint32))
+    finally:
+        g.close()
+
+
+def test_failed_keyframe_overwrite_keeps_the_old_keyframe(small_case):
+    """a failed liogpu_keyframe_put must neither leak nor delete the keyframe that was there"""
+    import ctypes as C
+    from lio_slam_b200.liogpu import LioGpu, E_INVALID
+    g = LioGpu()
+    try:
+        cloud = small_case["scan4"][:500]
+        g.keyframe_put(7, cloud)
+        pose = np.zeros((1, 6), np.float32)
+        before, _ = g.merge_keyframes([7], pose, 0.0)
+        st = g.lib.liogpu_keyframe_put(g.h, 7, cloud.ctypes.data, 500, 20)     # bad stride
+        assert st == E_INVALID
+        st = g.lib.liogpu_keyframe_put(g.h, 7, None, 500, 16)                   # null cloud
+        assert st == E_INVALID
+        after, _ = g.merge_keyframes([7], pose, 0.0)
+        assert g.keyframe_count() == 1 and np.array_equal(before.view(np.uint32), after.view(np.uint32))
+        g.keyframe_put(7, cloud[:100])                                          # a real overwrite still works, in place
+        again, _ = g.merge_keyframes([7], pose, 0.0)
+        assert again.shape[0] == 100
+    finally:
+        g.close()
+
+
+def test_fetch_result_serves_only_the_call_before_it(small_case):
+    import ctypes as C
+    from lio_slam_b200.liogpu import LioGpu, E_CAPACITY, E_INVALID
+    g = LioGpu()
+    try:
+        g.keyframe_put(0, small_case["scan4"])
+        pose = np.zeros((1, 6), np.float32)
+        ids = np.zeros(1, np.int32)
+        n = C.c_int(0)
+        tiny = np.empty((1, 4), np.float32)
+        st = g.lib.liogpu_merge_keyframes(g.h, ids.ctypes.data, pose.ctypes.data, 1, C.c_float(0.5), tiny.ctypes.data, 16, 1, C.byref(n))
+        assert st == E_CAPACITY and n.value > 1
+        out = np.empty((n.value, 4), np.float32)
+        assert g.lib.liogpu_fetch_result(g.h, out.ctypes.data, 16, n.value, C.byref(n)) == 0
+        want, _ = g.merge_keyframes([0], pose, 0.5)        # (this wrapper fetches too)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+        g.keyframe_count()
+        g.voxel_downsample(small_case["scan4"], 1.0)       # any other call invalidates the pending result
+        assert g.lib.liogpu_fetch_result(g.h, out.ctypes.data, 16, n.value, C.byref(n)) == E_INVALID
+    finally:
+        g.close()
