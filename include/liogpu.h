@@ -350,7 +350,8 @@ int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int strid
  * arrives (pcl::fromROSMsg, MO:440), BEFORE it takes `mtx` (MO:449): the copy then overlaps the registration of the
  * previous sweep, and the next call that names LIOGPU_UPLOADED_SCAN as its input waits for it on the device.  The
  * caller's buffer must stay valid until that call returns (pinned memory — liogpu_host_alloc — for a truly
- * asynchronous copy).  Two sweeps may be in flight.  Unlike every other entry point it may overlap ONE other call
+ * asynchronous copy).  Two sweeps may be in flight (a third returns LIOGPU_E_CAPACITY); consumers take them first in,
+ * first out.  Unlike every other entry point it may overlap ONE other call
  * on the same context. */
 int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int stride);
 

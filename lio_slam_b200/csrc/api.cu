@@ -47,10 +47,11 @@ int load_cloud(Ctx* c, const void* src, int& n, int stride, DevBuf& dst) {
     return LIOGPU_OK;
   }
   if (src == LIOGPU_UPLOADED_SCAN) {  // the sweep liogpu_upload_scan_async put on its way
-    if (c->upload_ready < 0 || !c->upload[c->upload_ready].valid) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
-    Ctx::Upload& u = c->upload[c->upload_ready];
+    if (c->upload_count <= 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    Ctx::Upload& u = c->upload[c->upload_head];  // first in, first out
     u.valid = false;
-    c->upload_ready = -1;
+    c->upload_head ^= 1;
+    c->upload_count--;
     n = u.n;
     LIOGPU_CUDA_OK(c, dst.reserve((size_t)(n > 0 ? n : 1) * sizeof(float4)));
     if (n == 0) return LIOGPU_OK;
@@ -410,7 +411,7 @@ int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int st
   if (!special && (n < 0 || (n > 0 && !xyzi) || !stride_ok(stride))) { c->err = "liogpu_keyframe_put: bad cloud pointer / size / stride"; return LIOGPU_E_INVALID; }
   int n_in = n;
   if (xyzi == LIOGPU_DEVICE_RESIDENT) { if (!c->resident) { c->err = "LIOGPU_DEVICE_RESIDENT: no resident cloud"; return LIOGPU_E_INVALID; } n_in = c->resident_n; }
-  if (xyzi == LIOGPU_UPLOADED_SCAN) { if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; } n_in = c->upload[c->upload_ready].n; }
+  if (xyzi == LIOGPU_UPLOADED_SCAN) { if (c->upload_count <= 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; } n_in = c->upload[c->upload_head].n; }
   DevBuf fresh;
   {
     auto old = c->keyframes.find(id);
@@ -787,8 +788,8 @@ int liogpu_scan2map(liogpu_ctx* ctx, const void* scan_ds, int n, int stride, flo
     n = c->resident_n;
   }
   if (scan_ds == LIOGPU_UPLOADED_SCAN) {
-    if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
-    n = c->upload[c->upload_ready].n;
+    if (c->upload_count <= 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    n = c->upload[c->upload_head].n;
   }
   rc = s2m_guards(c, n, info);
   if (rc) {
@@ -814,8 +815,8 @@ int liogpu_scan2map_trace(liogpu_ctx* ctx, const void* scan_ds, int n, int strid
     n = c->resident_n;
   }
   if (scan_ds == LIOGPU_UPLOADED_SCAN) {
-    if (c->upload_ready < 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
-    n = c->upload[c->upload_ready].n;
+    if (c->upload_count <= 0) { c->err = "LIOGPU_UPLOADED_SCAN: no upload pending"; return LIOGPU_E_INVALID; }
+    n = c->upload[c->upload_head].n;
   }
   rc = s2m_guards(c, n, info);
   if (rc) {
@@ -917,15 +918,15 @@ int liogpu_upload_scan_async(liogpu_ctx* ctx, const void* xyzi, int n, int strid
   // starts the copy when the message arrives, before it takes mtx)
   if (cudaSetDevice(c->device) != cudaSuccess) return LIOGPU_E_CUDA;
   if (n < 0 || (n > 0 && !xyzi) || !stride_ok(stride)) return LIOGPU_E_INVALID;
-  Ctx::Upload& u = c->upload[c->upload_next];
+  if (c->upload_count >= 2) return LIOGPU_E_CAPACITY;  // two sweeps already on their way
+  Ctx::Upload& u = c->upload[(c->upload_head + c->upload_count) & 1];
   if (u.raw.reserve((size_t)(n > 0 ? n : 1) * stride) != cudaSuccess) return LIOGPU_E_CUDA;
   if (n > 0 && cudaMemcpyAsync(u.raw.p, xyzi, (size_t)n * stride,
                                is_device_ptr(xyzi) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess)
     return LIOGPU_E_CUDA;
   if (cudaEventRecord(u.ev, c->copy_stream) != cudaSuccess) return LIOGPU_E_CUDA;
   u.n = n; u.stride = stride; u.valid = true;
-  c->upload_ready = c->upload_next;
-  c->upload_next ^= 1;
+  c->upload_count++;
   return LIOGPU_OK;
 }
 

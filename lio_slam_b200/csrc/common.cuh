@@ -167,7 +167,7 @@ struct Ctx {
   // liogpu_upload_scan_async: two staging slots filled on a copy stream
   cudaStream_t copy_stream = nullptr;
   struct Upload { DevBuf raw; cudaEvent_t ev = nullptr; int n = 0, stride = 0; bool valid = false; } upload[2];
-  int upload_next = 0, upload_ready = -1;
+  int upload_head = 0, upload_count = 0;  // FIFO: a consumer takes the OLDEST pending upload
 };
 
 #define LIOGPU_CUDA_OK(ctx, expr)                                                        \

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#include <memory>
 
 #include "map_optimization_gpu.h"
 
@@ -14,9 +15,47 @@ using namespace liorf_gpu;
 typedef std::chrono::steady_clock Clock;
 static inline double ms_since(const Clock::time_point& t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
 
+struct liorf_worker {
+  liogpu_params params;
+  liogpu_ctx* ctx;
+};
+
+static int replay_impl(const liogpu_params* params, liogpu_ctx* borrowed, const liorf_replay_options* options, const liorf_sweep* sweeps,
+                       int n, float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err, int err_len);
+
+extern "C" liorf_worker* liorf_worker_create(const liogpu_params* params, char* err, int err_len) {
+  if (err && err_len > 0) err[0] = 0;
+  if (!params) return nullptr;
+  liorf_worker* w = new liorf_worker();
+  w->params = *params;
+  w->ctx = nullptr;
+  if (liogpu_create(&w->ctx, params) != LIOGPU_OK) {
+    if (err && err_len > 0) std::snprintf(err, (size_t)err_len, "liogpu_create failed (no sm_100 GPU? there is no CPU fallback)");
+    delete w;
+    return nullptr;
+  }
+  return w;
+}
+extern "C" void liorf_worker_destroy(liorf_worker* w) {
+  if (!w) return;
+  liogpu_destroy(w->ctx);
+  delete w;
+}
+extern "C" int liorf_worker_replay(liorf_worker* w, const liorf_replay_options* options, const liorf_sweep* sweeps, int n,
+                                   float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err, int err_len) {
+  if (!w) return LIOGPU_E_INVALID;
+  const int rc = liogpu_keyframe_clear(w->ctx);  // a new sequence starts with an empty map
+  if (rc < 0) return rc;
+  return replay_impl(&w->params, w->ctx, options, sweeps, n, poses_out, iters_out, nds_out, stats, err, err_len);
+}
 extern "C" int liorf_replay_sequence(const liogpu_params* params, const liorf_replay_options* options, const liorf_sweep* sweeps,
                                      int n, float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err,
                                      int err_len) {
+  return replay_impl(params, nullptr, options, sweeps, n, poses_out, iters_out, nds_out, stats, err, err_len);
+}
+
+static int replay_impl(const liogpu_params* params, liogpu_ctx* borrowed, const liorf_replay_options* options, const liorf_sweep* sweeps,
+                       int n, float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err, int err_len) {
   if (err && err_len > 0) err[0] = 0;
   if (!params || !sweeps || n < 0) return LIOGPU_E_INVALID;
   liorf_replay_stats st;
@@ -26,7 +65,8 @@ extern "C" int liorf_replay_sequence(const liogpu_params* params, const liorf_re
   if (options) opt = *options;
   int rc = LIOGPU_OK;
   try {
-    mapOptimization MO(*params);
+    std::unique_ptr<mapOptimization> mo(borrowed ? new mapOptimization(*params, borrowed) : new mapOptimization(*params));
+    mapOptimization& MO = *mo;
     ImageProjection IP(MO.context());   // co-located nodes: one context, the deskewed sweep never leaves HBM
     MO.selectKeyPosesOnDevice = opt.select_key_poses_on_device != 0;
     if (opt.keyframe_dist > 0.f) MO.surroundingkeyframeAddingDistThreshold = opt.keyframe_dist;

@@ -50,6 +50,15 @@ int liorf_replay_sequence(const liogpu_params* params, const liorf_replay_option
                           int n, float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err,
                           int err_len);
 
+/* A mapping worker = one liogpu context (one GPU, one stream) that replays sequence after sequence: the context, its
+ * pinned staging memory and its device buffers are created once and reused (liogpu_keyframe_clear between sequences),
+ * as a batch-mapping service would do.  One worker per host thread. */
+typedef struct liorf_worker liorf_worker;
+liorf_worker* liorf_worker_create(const liogpu_params* params, char* err, int err_len);
+void liorf_worker_destroy(liorf_worker* w);
+int liorf_worker_replay(liorf_worker* w, const liorf_replay_options* options, const liorf_sweep* sweeps, int n,
+                        float* poses_out, int* iters_out, int* nds_out, liorf_replay_stats* stats, char* err, int err_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,11 @@ mapOptimization::mapOptimization(const liogpu_params& params) : params_(params) 
   if (st != LIOGPU_OK) throw std::runtime_error("liogpu_create failed (no sm_100 GPU? there is no CPU fallback)");
   liogpu_default_local_map_params(&localMapParams);  // utility.h:219-229
 }
-mapOptimization::~mapOptimization() { liogpu_destroy(ctx_); }
+mapOptimization::mapOptimization(const liogpu_params& params, liogpu_ctx* borrowed) : ctx_(borrowed), owns_ctx_(false), params_(params) {
+  if (!ctx_) throw std::runtime_error("mapOptimization: null context");
+  liogpu_default_local_map_params(&localMapParams);
+}
+mapOptimization::~mapOptimization() { if (owns_ctx_) liogpu_destroy(ctx_); }
 const char* mapOptimization::lastError() const { return liogpu_last_error(ctx_); }
 
 static inline float pointDistance(const PointType& a, const PointType& b) {  // common_lib.cpp:33-37

@@ -62,6 +62,8 @@ class ImageProjection {
 class mapOptimization {
  public:
   explicit mapOptimization(const liogpu_params& params);
+  // the same node around a context owned by somebody else (a mapping worker that replays one sequence after another)
+  mapOptimization(const liogpu_params& params, liogpu_ctx* borrowed);
   ~mapOptimization();
   mapOptimization(const mapOptimization&) = delete;
 
@@ -120,6 +122,7 @@ class mapOptimization {
 
  private:
   liogpu_ctx* ctx_ = nullptr;
+  bool owns_ctx_ = true;
   liogpu_params params_;
   std::vector<int> mapKeyIds_;  // keyframe set the device-resident local map was built from
   std::vector<float> mapKeyPoses_;

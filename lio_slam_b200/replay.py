@@ -47,6 +47,12 @@ def load_host_library() -> C.CDLL:
     lib.liorf_replay_sequence.argtypes = [C.POINTER(liogpu.Params), C.POINTER(ReplayOptions), C.POINTER(Sweep), C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ReplayStats), C.c_char_p, C.c_int]
     lib.liorf_replay_sequence.restype = C.c_int
+    lib.liorf_worker_create.argtypes = [C.POINTER(liogpu.Params), C.c_char_p, C.c_int]
+    lib.liorf_worker_create.restype = C.c_void_p
+    lib.liorf_worker_destroy.argtypes = [C.c_void_p]
+    lib.liorf_worker_replay.argtypes = [C.c_void_p, C.POINTER(ReplayOptions), C.POINTER(Sweep), C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.POINTER(ReplayStats), C.c_char_p, C.c_int]
+    lib.liorf_worker_replay.restype = C.c_int
     _lib = lib
     return lib
 
@@ -60,7 +66,32 @@ def kitti_params(device: int = 0, **over) -> liogpu.Params:
     return liogpu.default_params(**kw)
 
 
-def replay_sequence(params: liogpu.Params, seq: dict, first: int = 0, count: int | None = None, **options):
+class Worker:
+    """liorf_worker: one liogpu context reused for sequence after sequence (one per host thread)."""
+
+    def __init__(self, params: liogpu.Params):
+        self.lib = load_host_library()
+        err = C.create_string_buffer(256)
+        self.h = self.lib.liorf_worker_create(C.byref(params), err, 256)
+        if not self.h:
+            raise liogpu.LioGpuError(liogpu.E_CUDA, err.value.decode() or "liorf_worker_create failed")
+
+    def replay(self, seq: dict, first: int = 0, count: int | None = None, **options):
+        return replay_sequence(None, seq, first, count, _worker=self, **options)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.liorf_worker_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def replay_sequence(params, seq: dict, first: int = 0, count: int | None = None, _worker: "Worker | None" = None, **options):
     """seq: the dict of synth_torch.make_sequence (raw pinned tensor or numpy uint8/float32 array of 32-byte records,
     offs, times, guesses, imu).  -> (poses (n,6) f32, iterations (n,), n_ds (n,), stats dict)"""
     lib = load_host_library()
@@ -91,8 +122,12 @@ def replay_sequence(params: liogpu.Params, seq: dict, first: int = 0, count: int
     nds = np.zeros(n, np.int32)
     stats = ReplayStats()
     err = C.create_string_buffer(512)
-    rc = lib.liorf_replay_sequence(C.byref(params), C.byref(opt), sweeps, n, poses.ctypes.data, iters.ctypes.data,
-                                   nds.ctypes.data, C.byref(stats), err, 512)
+    if _worker is not None:
+        rc = lib.liorf_worker_replay(_worker.h, C.byref(opt), sweeps, n, poses.ctypes.data, iters.ctypes.data,
+                                     nds.ctypes.data, C.byref(stats), err, 512)
+    else:
+        rc = lib.liorf_replay_sequence(C.byref(params), C.byref(opt), sweeps, n, poses.ctypes.data, iters.ctypes.data,
+                                       nds.ctypes.data, C.byref(stats), err, 512)
     if rc != 0:
         raise liogpu.LioGpuError(rc, err.value.decode() or "liorf_replay_sequence failed")
     d = {k: getattr(stats, k) for k, _ in ReplayStats._fields_ if k != "reserved"}

@@ -392,11 +392,15 @@ def test_upload_scan_async_equals_direct_call(small_case, oracle):
         g.upload_scan_async(rec)
         got_pose, _, got = g.scan2map(UPLOADED, small_case["guess"])
         assert got["iterations"] == want["iterations"] and np.array_equal(got_pose.view(np.uint32), want_pose.view(np.uint32))
-        # two sweeps in flight, consumed... the newest upload is the one a consumer sees; packed stride works too
+        # two sweeps in flight are consumed first in, first out; a third is refused; packed stride works too
+        half = np.ascontiguousarray(ds[: ds.shape[0] // 2])
         g.upload_scan_async(ds)
-        n_ds, st = g.voxel_downsample(UPLOADED, 0.8, keep_on_device=True)
-        ref, _ = oracle.voxel_grid(ds, 0.8)
-        assert n_ds == ref.shape[0]
+        g.upload_scan_async(half)
+        with pytest.raises(LioGpuError):
+            g.upload_scan_async(ds)
+        n_a, st = g.voxel_downsample(UPLOADED, 0.8, keep_on_device=True)
+        n_b, st = g.voxel_downsample(UPLOADED, 0.8, keep_on_device=True)
+        assert n_a == oracle.voxel_grid(ds, 0.8)[0].shape[0] and n_b == oracle.voxel_grid(half, 0.8)[0].shape[0]
     finally:
         g.close()
 

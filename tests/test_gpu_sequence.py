@@ -148,3 +148,21 @@ def test_kitti_sequence_replay_matches_oracle_scan_by_scan(oracle, world, on_dev
           f"keyframes {st['keyframes']}, map rebuilds {st['map_rebuilds']}, wall {st['wall_ms'] / n:.3f} ms/scan "
           f"(deskew {st['deskew_ms'] / n:.3f}, nearby+map {st['nearby_ms'] / n:.3f}, register {st['register_ms'] / n:.3f}, "
           f"keyframe {st['keyframe_ms'] / n:.3f}), launches/scan {st['gpu_launches'] / n:.0f}, oracle {wst['wall_ms'] / n:.1f} ms/scan")
+
+
+def test_mapping_worker_reuses_its_context_across_sequences(world):
+    """liorf_worker: sequence after sequence on ONE context must give exactly what fresh contexts give"""
+    import torch
+    from lio_slam_b200 import replay, synth_torch
+    dev = torch.device("cuda", 0)
+    seqs = [synth_torch.make_sequence(world, 64, 20, seed=21 + s, device=dev, step=0.35, s0=3.0 * s) for s in range(2)]
+    prm = replay.kitti_params()
+    fresh = [replay.replay_sequence(prm, q) for q in seqs]
+    wk = replay.Worker(prm)
+    try:
+        again = [wk.replay(q) for q in seqs] + [wk.replay(seqs[0])]
+    finally:
+        wk.close()
+    for a, b in zip(fresh + [fresh[0]], again):
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert a[3]["keyframes"] == b[3]["keyframes"]
