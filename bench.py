@@ -393,40 +393,49 @@ def bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank
                     "tile's sort + centroids shrink with N"}
 
 
-def bench_cfg5(torch, dist, rank, world_size, local_rank, n_seq=8, n_scans=200, concurrency=0):
-    """configs[4]: 8 independent 64-beam sequences through the host mirror's per-scan path, strong scaling."""
+def bench_cfg5(torch, dist, rank, world_size, local_rank, n_seq=8, n_scans=200, concurrency=0, weak=True):
+    """configs[4]: 8 independent 64-beam sequences through the host mirror's per-scan path.  Strong scaling: the 8
+    sequences are dealt round-robin to the N ranks.  Weak companion: every rank replays all 8 (its own copy), which
+    shows what N GPUs deliver when each is fed as well as the single GPU of the strong N = 1 run."""
     from lio_slam_b200 import replay, sharding, synth, synth_torch
     dev = torch.device("cuda", local_rank)
     world = synth.make_world(1234)
     my = sharding.assign_sequences(n_seq, world_size, rank)
-    seqs = {s: synth_torch.make_sequence(world, 64, n_scans, seed=11 + s, device=dev, step=0.35, s0=2.0 * s) for s in my}
+    need = list(range(n_seq)) if weak else my
+    seqs = {s: synth_torch.make_sequence(world, 64, n_scans, seed=11 + s, device=dev, step=0.35, s0=2.0 * s) for s in need}
     prm = replay.kitti_params(device=local_rank)
     replay.load_host_library()
-    conc = len(my) if concurrency <= 0 else min(concurrency, len(my))
-    # mapping workers (one liogpu context + host thread each) exist before the job starts, like a mapping service's
-    # pool; every worker replays its share of the rank's sequences one after another on its own context
-    workers = [replay.Worker(prm) for _ in range(max(conc, 1))]
-    for wk in workers:   # warm-up: buffers find their size, kernels are loaded, clocks ramp (not timed)
-        if my:
-            wk.replay(seqs[my[0]], count=min(30, n_scans))
-    results = {}
 
-    def run(wk, mine):
-        for s in mine:
-            results[s] = wk.replay(seqs[s])
+    def job(which, conc):
+        """replay the sequences `which` on `conc` workers of this rank -> (wall s, results)"""
+        conc = max(1, min(conc, len(which)))
+        # mapping workers (one liogpu context + host thread each) exist before the job starts, like a mapping
+        # service's pool; every worker replays its share of the sequences one after another on its own context
+        workers = [replay.Worker(prm) for _ in range(conc)]
+        for wk in workers:   # warm-up: buffers find their size, kernels are loaded, clocks ramp (not timed)
+            wk.replay(seqs[which[0]], count=min(30, n_scans))
+        results = {}
 
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    ths = [threading.Thread(target=run, args=(workers[j], my[j::max(conc, 1)])) for j in range(max(conc, 1))]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
-    wall = time.perf_counter() - t0
-    for wk in workers:
-        wk.close()
+        def run(wk, mine):
+            for s in mine:
+                results[s] = wk.replay(seqs[s])
+
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=run, args=(workers[j], which[j::conc])) for j in range(conc)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        wall = time.perf_counter() - t0
+        for wk in workers:
+            wk.close()
+        return wall, results, conc
+
+    conc_req = len(my) if concurrency <= 0 else concurrency
+    wall, results, conc = job(my, conc_req)
     agg = torch.tensor([wall], dtype=torch.float64, device=dev)
     sums = torch.zeros(10, dtype=torch.float64, device=dev)
     for s in my:
@@ -445,20 +454,35 @@ def bench_cfg5(torch, dist, rank, world_size, local_rank, n_seq=8, n_scans=200, 
         dist.all_reduce(errt, op=dist.ReduceOp.MAX)
     wall = float(agg[0]); v = sums.tolist()
     scans = v[0]
-    return {"workload": f"cfg5: batch offline mapping, {n_seq} independent 64-beam sequences x {n_scans} sweeps (configs[4]; kitti.yaml: "
-                        f"downsampleRate 2, point_filter_num 5, leaves 0.4 / 0.5), full per-scan path through the host mirror",
-            "n_gpus": world_size, "scaling": "strong", "sequences": n_seq, "scans_per_sequence": n_scans,
-            "sequences_per_rank_concurrent": conc, "total_scans": int(scans), "wall_s": wall,
-            "value": scans / wall, "unit": "scans/s (whole job, wall clock, sweep uploads and read-backs inside)",
-            "registered": int(v[1]), "keyframes": int(v[2]), "local_map_rebuilds": int(v[3]),
-            "mean_lm_iterations": v[4] / max(v[1], 1.0),
-            "host_ms_per_scan": {"deskew_upload": v[5] / scans, "extract_nearby_and_rebuild": v[6] / scans,
-                                 "downsample_register": v[7] / scans, "keyframe": v[8] / scans},
-            "gpu_launches_per_scan": v[9] / scans,
-            "h2d_bytes_per_scan": float(bytes_[0]) / scans, "d2h_bytes_per_scan": float(bytes_[1]) / scans,
-            "max_position_error_vs_ground_truth_m": float(errt[0]),
-            "note": ("1000 sweeps per sequence do not fit the bench's time limit (generation alone); "
-                     f"{n_scans} are replayed" if n_scans < 1000 else "")}, seqs, prm
+    rec = {"workload": f"cfg5: batch offline mapping, {n_seq} independent 64-beam sequences x {n_scans} sweeps (configs[4]; kitti.yaml: "
+                       f"downsampleRate 2, point_filter_num 5, leaves 0.4 / 0.5), full per-scan path through the host mirror",
+           "n_gpus": world_size, "scaling": "strong", "sequences": n_seq, "scans_per_sequence": n_scans,
+           "workers_per_rank": conc, "total_scans": int(scans), "wall_s": wall,
+           "value": scans / wall, "unit": "scans/s (whole job, wall clock, sweep uploads and read-backs inside)",
+           "registered": int(v[1]), "keyframes": int(v[2]), "local_map_rebuilds": int(v[3]),
+           "mean_lm_iterations": v[4] / max(v[1], 1.0),
+           "host_ms_per_scan": {"deskew_upload": v[5] / scans, "extract_nearby_and_rebuild": v[6] / scans,
+                                "downsample_register": v[7] / scans, "keyframe": v[8] / scans},
+           "gpu_launches_per_scan": v[9] / scans,
+           "h2d_bytes_per_scan": float(bytes_[0]) / scans, "d2h_bytes_per_scan": float(bytes_[1]) / scans,
+           "max_position_error_vs_ground_truth_m": float(errt[0]),
+           "note": ("a sequence is a serial chain of latency-bound scans (one worker keeps a B200 ~15 % busy), so ONE GPU already runs "
+                    "the 8 sequences concurrently; spreading them over N GPUs leaves 8/N workers per GPU. "
+                    + (f"1000 sweeps per sequence do not fit the bench's time limit (input generation alone); {n_scans} are replayed"
+                       if n_scans < 1000 else ""))}
+    if weak:
+        cores = os.cpu_count() or 8
+        wconc = max(1, min(n_seq, cores // max(world_size, 1)))
+        wwall, wres, wconc = job(list(range(n_seq)), wconc)
+        wt = torch.tensor([wwall], dtype=torch.float64, device=dev)
+        ws = torch.tensor([float(sum(wres[s][3]["scans"] for s in wres))], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX); dist.all_reduce(ws)
+        rec["weak_companion"] = {"scaling": "weak", "sequences_per_gpu": n_seq, "workers_per_rank": wconc,
+                                 "total_scans": int(ws[0]), "wall_s": float(wt[0]), "value": float(ws[0]) / float(wt[0]),
+                                 "unit": "scans/s (whole job)",
+                                 "note": "every rank replays all 8 sequences: N x the work of the strong N = 1 run"}
+    return rec, seqs, prm
 
 
 def cpu_cfg5_sample(seq, n=40):
@@ -541,7 +565,8 @@ def main():
         if args.only == "cfg4":
             rec = bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank)
         else:
-            rec = bench_cfg5(torch, dist, rank, world_size, local_rank, n_scans=args.seq_scans, concurrency=args.seq_concurrency)[0]
+            rec = bench_cfg5(torch, dist, rank, world_size, local_rank, n_scans=args.seq_scans, concurrency=args.seq_concurrency,
+                             weak=world_size > 1)[0]
         if rank == 0:
             print(json.dumps(rec))
         if dist is not None:
@@ -610,7 +635,7 @@ def main():
         extras["cfg4"] = bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank)
         barrier()
         extras["cfg5"], cfg5_seqs, _ = bench_cfg5(torch, dist, rank, world_size, local_rank, n_scans=args.seq_scans,
-                                                  concurrency=args.seq_concurrency)
+                                                  concurrency=args.seq_concurrency, weak=world_size > 1)
         if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
             cb1 = cpu_baseline_run("cfg1", m1, s1, g1, args.cpu_steps, 3)
             extras["cfg1"]["cpu_baseline"] = cb1
