@@ -1,4 +1,6 @@
 // sort.cu — hand-written stable LSD radix sort of (u32 key, u32 value) pairs and a u32 exclusive scan.
+// (Round 2: radix_sort_pairs runs the one-sweep kernels further down; the three-launch pass of round 1 is kept as
+//  radix_sort_pairs_3launch for A/B — `LIOGPU_SORT=3launch` selects it at run time.)
 //
 // Used by the VoxelGrid replacement (pcl::VoxelGrid sorts (voxel idx, point idx) pairs; SURVEY A.1
 // step 6 — the canonical order is the STABLE one, which is what an LSD radix sort delivers) and by
@@ -11,6 +13,7 @@
 //   rs_scatter_kernel stable multi-split: warp-level match_any ranking in firing order, then scatter
 // HBM traffic per pass: read 8n (hist reads keys only: 4n) + read 8n + write 8n bytes.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace liogpu {
 
@@ -159,6 +162,210 @@ __global__ void iota_kernel(uint32_t* v, int n) {
   if (i < n) v[i] = (uint32_t)i;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round 2: one-sweep LSD radix sort (chained scan with decoupled look-back).  Same contract as the three-launch
+// pass above (stable, 8-bit digits, ping-pong buffers) with ONE launch per pass:
+//   os_hist_kernel   one pass over the keys: the digit histograms of ALL passes (shared-memory atomics, then global);
+//                    the last block turns each into exclusive digit bases
+//   os_pass_kernel   a CTA takes the next tile (atomic ticket, so a tile only ever waits for tiles that already hold
+//                    an SM), ranks its 2048 keys (warp-level match_any, firing order), publishes its per-digit counts
+//                    and finds its global offsets by looking back at its predecessors' status words
+//                    (00 empty | 01 count of this tile | 10 inclusive prefix), stages the tile in digit order in shared
+//                    memory and writes every digit's run with consecutive lanes (coalesced), instead of one scattered
+//                    4-byte store per key.
+// Launches per sort: memset + histogram + passes (6 for 32-bit keys, was 12); bytes per pass: 16n (was 24n).
+constexpr uint32_t OS_VALUE_MASK = 0x3fffffffu;
+constexpr uint32_t OS_AGGREGATE = 1u << 30, OS_PREFIX = 2u << 30;
+
+__device__ __forceinline__ uint32_t os_ld(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void os_st(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ghist[pass][256] (zeroed); ticket (zeroed).  On return ghist holds exclusive digit bases.
+__global__ void __launch_bounds__(RS_THREADS)
+os_hist_kernel(const uint32_t* __restrict__ keys, int n, int passes, uint32_t* __restrict__ ghist, uint32_t* __restrict__ ticket) {
+  __shared__ uint32_t h[4][256];
+  __shared__ bool last;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) h[p][t] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * RS_THREADS + t; i < n; i += (long long)gridDim.x * RS_THREADS) {
+    const uint32_t k = keys[i];
+    atomicAdd(&h[0][k & 255u], 1u);
+    if (passes > 1) atomicAdd(&h[1][(k >> 8) & 255u], 1u);
+    if (passes > 2) atomicAdd(&h[2][(k >> 16) & 255u], 1u);
+    if (passes > 3) atomicAdd(&h[3][k >> 24], 1u);
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p)
+    if (h[p][t]) atomicAdd(&ghist[p * 256 + t], h[p][t]);
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  __shared__ uint32_t wsum[RS_WARPS];
+  const int lane = t & 31, w = t >> 5;
+  for (int p = 0; p < passes; ++p) {  // exclusive scan of the 256 totals of pass p
+    const uint32_t v = __ldcg(ghist + p * 256 + t);
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int k = 0; k < w; ++k) base += wsum[k];
+    ghist[p * 256 + t] = base + x - v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,  // vals_in may be null: iota
+               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
+               const uint32_t* __restrict__ gbase, uint32_t* __restrict__ status, uint32_t* __restrict__ tile_ticket,
+               const int* __restrict__ d_key_bits) {
+  __shared__ uint32_t warp_hist[RS_WARPS][256];
+  __shared__ uint32_t s_cnt[256], s_lstart[256], s_gpos[256];
+  __shared__ uint32_t s_key[RS_TILE], s_val[RS_TILE];
+  __shared__ uint32_t s_wsum[RS_WARPS];
+  __shared__ int s_tile;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) s_tile = (int)atomicAdd(tile_ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const long long begin = (long long)tile * RS_TILE;
+  long long end = begin + RS_TILE;
+  if (end > n) end = n;
+  if (d_key_bits && shift >= *d_key_bits) {
+    // every remaining digit is zero: the pass would be the identity permutation — just move the data
+    for (long long i = begin + t; i < end; i += RS_THREADS) {
+      keys_out[i] = keys_in[i];
+      vals_out[i] = vals_in ? vals_in[i] : (uint32_t)i;
+    }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; ++k) warp_hist[k][t] = 0;
+  __syncthreads();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const long long idx = begin + (long long)w * (32 * RS_ITEMS) + it * 32 + lane;
+    const bool valid = idx < end;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    key[it] = 0; val[it] = 0; rank[it] = 0;
+    if (valid) {
+      key[it] = keys_in[idx];
+      val[it] = vals_in ? vals_in[idx] : (uint32_t)idx;
+      const uint32_t d = (key[it] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(act, d);
+      const uint32_t pre = warp_hist[w][d];
+      __syncwarp(act);
+      if ((peers & lt_mask) == 0) warp_hist[w][d] = pre + __popc(peers);
+      __syncwarp(act);
+      rank[it] = pre + __popc(peers & lt_mask);
+    }
+  }
+  __syncthreads();
+  // per digit (thread = digit): exclusive prefix over the warps, the tile's count, the chained scan
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int k = 0; k < RS_WARPS; ++k) {
+    const uint32_t c = warp_hist[k][t];
+    warp_hist[k][t] = cnt;
+    cnt += c;
+  }
+  uint32_t* my_status = status + (size_t)tile * 256 + t;
+  os_st(my_status, (tile == 0 ? OS_PREFIX : OS_AGGREGATE) | cnt);
+  uint32_t excl = 0;
+  for (int p = tile - 1; p >= 0;) {
+    const uint32_t v = os_ld(status + (size_t)p * 256 + t);
+    const uint32_t flag = v & ~OS_VALUE_MASK;
+    if (flag == 0) continue;  // predecessor has not published yet (it holds an SM: the ticket order guarantees progress)
+    excl += v & OS_VALUE_MASK;
+    if (flag == OS_PREFIX) break;
+    --p;
+  }
+  if (tile > 0) os_st(my_status, OS_PREFIX | (excl + cnt));
+  s_cnt[t] = cnt;
+  s_gpos[t] = gbase[t] + excl;
+  {  // tile-local exclusive scan over the digits
+    uint32_t x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_wsum[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int k = 0; k < w; ++k) base += s_wsum[k];
+    s_lstart[t] = base + x - cnt;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const long long idx = begin + (long long)w * (32 * RS_ITEMS) + it * 32 + lane;
+    if (idx < end) {
+      const uint32_t d = (key[it] >> shift) & 255u;
+      const uint32_t lp = s_lstart[d] + warp_hist[w][d] + rank[it];
+      s_key[lp] = key[it];
+      s_val[lp] = val[it];
+    }
+  }
+  __syncthreads();
+  const int tile_n = (int)(end - begin);
+  for (int j = t; j < tile_n; j += RS_THREADS) {
+    const uint32_t k = s_key[j];
+    const uint32_t d = (k >> shift) & 255u;
+    const uint32_t pos = s_gpos[d] + ((uint32_t)j - s_lstart[d]);
+    keys_out[pos] = k;
+    vals_out[pos] = s_val[j];
+  }
+}
+
+// The round-1 driver (three launches per pass), kept for A/B runs: LIOGPU_SORT=3launch
+static cudaError_t radix_sort_pairs_3launch(Ctx* c, int n, int key_bits, const int* d_key_bits, uint32_t** keys_out,
+                                            uint32_t** vals_out) {
+  uint32_t* k[2] = {c->keys0.as<uint32_t>(), c->keys1.as<uint32_t>()};
+  uint32_t* v[2] = {c->vals0.as<uint32_t>(), c->vals1.as<uint32_t>()};
+  const int passes = key_bits >= 0 ? (key_bits + 7) / 8 : 4;
+  if (key_bits >= 0) d_key_bits = nullptr;
+  int cur = 0;
+  const int tiles = div_up(n, RS_TILE);
+  const int nblocks = tiles < RS_MAX_BLOCKS ? tiles : RS_MAX_BLOCKS;
+  const int tiles_per_block = div_up(tiles, nblocks);
+  const int nb = div_up(tiles, tiles_per_block);
+  cudaError_t e = c->counters.reserve((size_t)(256 * (size_t)nb + 256) * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  uint32_t* counters = c->counters.as<uint32_t>();
+  uint32_t* digit_total = counters + (size_t)256 * nb;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    rs_hist_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], n, shift, tiles_per_block, counters, nb, d_key_bits);
+    rs_scan_kernel<<<256, 1024, 0, c->stream>>>(counters, nb, digit_total, shift, d_key_bits);
+    rs_scatter_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], p == 0 ? nullptr : v[cur], k[cur ^ 1], v[cur ^ 1], n,
+                                                        shift, tiles_per_block, counters, nb, digit_total, d_key_bits);
+    c->launches += 3;
+    cur ^= 1;
+  }
+  *keys_out = k[cur];
+  *vals_out = v[cur];
+  return cudaGetLastError();
+}
+
 // Sort the n pairs whose keys are in c->keys0 (values implicit iota on the first pass).  On return
 // *keys_out / *vals_out point at whichever ping-pong buffer holds the result.
 // key_bits >= 0: the host knows the key width and runs ceil(key_bits/8) passes.
@@ -178,21 +385,26 @@ cudaError_t radix_sort_pairs(Ctx* c, int n, int key_bits, const int* d_key_bits,
     *keys_out = k[0]; *vals_out = v[0];
     return cudaGetLastError();
   }
+  static const bool use_3launch = [] { const char* e = getenv("LIOGPU_SORT"); return e && !strcmp(e, "3launch"); }();
+  if (use_3launch || n >= (1 << 30)) return radix_sort_pairs_3launch(c, n, key_bits, d_key_bits, keys_out, vals_out);
   const int tiles = div_up(n, RS_TILE);
-  const int nblocks = tiles < RS_MAX_BLOCKS ? tiles : RS_MAX_BLOCKS;
-  const int tiles_per_block = div_up(tiles, nblocks);
-  const int nb = div_up(tiles, tiles_per_block);
-  cudaError_t e = c->counters.reserve((size_t)(256 * (size_t)nb + 256) * sizeof(uint32_t));
+  // scratch: [4][256] digit bases | 8 tickets | [passes][tiles][256] status words, zeroed in one memset
+  const size_t words = 4 * 256 + 8 + (size_t)passes * (size_t)tiles * 256;
+  cudaError_t e = c->counters.reserve(words * sizeof(uint32_t));
   if (e != cudaSuccess) return e;
-  uint32_t* counters = c->counters.as<uint32_t>();
-  uint32_t* digit_total = counters + (size_t)256 * nb;
+  uint32_t* ghist = c->counters.as<uint32_t>();
+  uint32_t* tickets = ghist + 4 * 256;
+  uint32_t* status = tickets + 8;
+  e = cudaMemsetAsync(ghist, 0, words * sizeof(uint32_t), c->stream);
+  if (e != cudaSuccess) return e;
+  int hist_blocks = tiles < c->sm_count * 8 ? tiles : c->sm_count * 8;
+  os_hist_kernel<<<hist_blocks, RS_THREADS, 0, c->stream>>>(k[0], n, passes, ghist, tickets);
+  c->launches++;
   for (int p = 0; p < passes; ++p) {
-    const int shift = 8 * p;
-    rs_hist_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], n, shift, tiles_per_block, counters, nb, d_key_bits);
-    rs_scan_kernel<<<256, 1024, 0, c->stream>>>(counters, nb, digit_total, shift, d_key_bits);
-    rs_scatter_kernel<<<nb, RS_THREADS, 0, c->stream>>>(k[cur], p == 0 ? nullptr : v[cur], k[cur ^ 1], v[cur ^ 1], n,
-                                                        shift, tiles_per_block, counters, nb, digit_total, d_key_bits);
-    c->launches += 3;
+    os_pass_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(k[cur], p == 0 ? nullptr : v[cur], k[cur ^ 1], v[cur ^ 1], n, 8 * p,
+                                                       ghist + p * 256, status + (size_t)p * tiles * 256, tickets + 1 + p,
+                                                       d_key_bits);
+    c->launches++;
     cur ^= 1;
   }
   *keys_out = k[cur];
