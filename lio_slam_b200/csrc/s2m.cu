@@ -599,8 +599,25 @@ __device__ __forceinline__ void warp_refresh_transform(LmDevState* st, const int
     st->trig[0] = B; st->trig[1] = A; st->trig[2] = D; st->trig[3] = C; st->trig[4] = F; st->trig[5] = E;
   }
 }
-__global__ void lm_prepare_kernel(LmDevState* st) {
-  if (blockIdx.x == 0 && threadIdx.x < 32) warp_refresh_transform(st, threadIdx.x, threadIdx.x < 6 ? st->pose[threadIdx.x] : 0.f);
+// The loop's initial state travels as LAUNCH PARAMETERS, not as a host-to-device copy: a copy would queue on the copy
+// engine behind a sweep upload that may be in flight (liogpu_upload_scan_async) and hold the whole loop back.
+struct LmInit {
+  float pose[6];
+  float matP[36];
+  int degenerate;
+  int max_iter;
+};
+__global__ void __launch_bounds__(256)
+lm_prepare_kernel(LmDevState* st, const LmInit init) {
+  if (blockIdx.x != 0) return;
+  unsigned* w = reinterpret_cast<unsigned*>(st);
+  for (int k = threadIdx.x; k < (int)(sizeof(LmDevState) / sizeof(unsigned)); k += blockDim.x) w[k] = 0u;
+  __syncthreads();
+  if (threadIdx.x < 6) st->pose[threadIdx.x] = init.pose[threadIdx.x];
+  if (threadIdx.x < 36) st->matP[threadIdx.x] = init.matP[threadIdx.x];
+  if (threadIdx.x == 40) { st->degenerate = init.degenerate; st->max_iter = init.max_iter; }
+  __syncthreads();
+  if (threadIdx.x < 32) warp_refresh_transform(st, threadIdx.x, threadIdx.x < 6 ? init.pose[threadIdx.x] : 0.f);
 }
 
 // lambda_min(A) > mu  <=>  A - mu*I is positive definite  <=>  its LDL^T has positive pivots (f64, static
@@ -808,6 +825,8 @@ struct S2mArgs {
   SurfDebugOut dbg;
   int mode;
   int main_blocks;
+  int seg_stride;          // slots per segment of fail_seg (S2M_THREADS, or 32 for the persistent-warp main kernel)
+  unsigned* queue;         // chunk queue head of the persistent-warp main kernel
   int* prev_nn;            // [5][nq] neighbours found by the previous iteration (-1: none), SoA
   float4* hopeless;        // [nq] (x,y,z of the point when it was found hopeless, w = 1) or w = 0
 };
@@ -870,37 +889,10 @@ __device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, cons
   }
 }
 
-__global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
-s2m_main_kernel(const S2mArgs A) {
-  __shared__ float sT[12];
-  __shared__ LmTrig sTrig;
-  __shared__ float rows[S2M_THREADS][8];  // 6 Jacobian entries, rhs, accepted flag
-  __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
-  __shared__ int s_ties, s_wfail[S2M_THREADS / 32], s_iter, s_seeded;
-  __shared__ bool s_last;
-
-  __shared__ int s_done0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream
-  // was still in its single-block tail; nothing it wrote may be read before this returns.
-  cudaGridDependencySynchronize();
-  if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
-  if (tid == 32) {
-    sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
-    sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
-    s_ties = 0;
-    s_seeded = 0;
-  }
-  if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
-  __syncthreads();
-  if (A.mode == 0 && s_done0) return;
-
-  const int i = blockIdx.x * S2M_THREADS + tid;
-  float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float rhs = 0.f;
-  bool flag = false, tie = false, need2 = false;
-  int seeded = 0;
-  if (i < A.nq) {
+// One sweep point of surfOptimization: transform, exact search (phase-1 gate, seeded bound or skip), plane fit, Jacobian row.
+// need2: the phase-1 gate could not settle the point (it goes to the leftover list).
+__device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, const LmTrig& sTrig, const int s_iter, const int i,
+                                           float row[6], float& rhs, bool& flag, bool& tie, bool& need2, int& seeded) {
     const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
     Top5 t;
@@ -952,7 +944,39 @@ s2m_main_kernel(const S2mArgs A) {
       need2 = true;
     }
     if (!need2) finish_point(A, i, ori, sel, t, sTrig, row, rhs, flag, tie);
+}
+
+__global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
+s2m_main_kernel(const S2mArgs A) {
+  __shared__ float sT[12];
+  __shared__ LmTrig sTrig;
+  __shared__ float rows[S2M_THREADS][8];  // 6 Jacobian entries, rhs, accepted flag
+  __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
+  __shared__ int s_ties, s_wfail[S2M_THREADS / 32], s_iter, s_seeded;
+  __shared__ bool s_last;
+
+  __shared__ int s_done0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream
+  // was still in its single-block tail; nothing it wrote may be read before this returns.
+  cudaGridDependencySynchronize();
+  if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
+  if (tid == 32) {
+    sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
+    sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
+    s_ties = 0;
+    s_seeded = 0;
   }
+  if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
+  __syncthreads();
+  if (A.mode == 0 && s_done0) return;
+
+  const int i = blockIdx.x * S2M_THREADS + tid;
+  float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float rhs = 0.f;
+  bool flag = false, tie = false, need2 = false;
+  int seeded = 0;
+  if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded);
   // leftover indices, in thread order, into this block's segment
   const unsigned fm = __ballot_sync(0xffffffffu, need2);
   if (lane == 0) s_wfail[warp] = __popc(fm);
@@ -1036,6 +1060,101 @@ s2m_main_kernel(const S2mArgs A) {
   }
 }
 
+// Persistent-warp variant of s2m_main_kernel (round 2, VERDICT lever (i)): the grid is sized to residency and every
+// WARP pulls 32-point chunks from an atomic queue until the sweep is exhausted, so no SM idles while work remains (the
+// fixed grid left 23 % of the SM-cycles idle: 900 CTAs on 592 slots).  A chunk's 27 sums go to its own partial row and
+// its leftovers to its own segment (both indexed by the chunk, so the result does not depend on which warp took it);
+// the last CTA to finish turns the per-chunk leftover counts into offsets, exactly as the fixed-grid kernel does per block.
+__global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
+s2m_main_pw_kernel(const S2mArgs A) {
+  __shared__ float sT[12];
+  __shared__ LmTrig sTrig;
+  __shared__ float rows[S2M_THREADS][8];
+  __shared__ int s_iter, s_done0;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cudaGridDependencySynchronize();
+  if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];
+  if (tid == 32) {
+    sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
+    sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
+  }
+  if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
+  __syncthreads();
+  if (A.mode == 0 && s_done0) return;
+  const int nchunks = A.main_blocks;
+  const RowAcc ra = row_acc_of(lane);
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = (int)atomicAdd(A.queue, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) break;
+    const int i = c * 32 + lane;
+    float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float rhs = 0.f;
+    bool flag = false, tie = false, need2 = false;
+    int seeded = 0;
+    if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded);
+    const unsigned fm = __ballot_sync(0xffffffffu, need2);
+    if (need2) A.fail_seg[(size_t)c * 32 + __popc(fm & ((1u << lane) - 1u))] = i;
+    if (lane == 0) A.block_nfail[c] = __popc(fm);
+    const int w_ties = __popc(__ballot_sync(0xffffffffu, flag && tie));
+    const int w_seed = __popc(__ballot_sync(0xffffffffu, seeded != 0));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rows[tid][k] = row[k];
+    rows[tid][6] = rhs;
+    rows[tid][7] = flag ? 1.f : 0.f;
+    __syncwarp();
+    double acc = 0.0;
+    if (ra.live) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float* rr = rows[warp * 32 + r];
+        acc += (double)rr[ra.a] * (double)rr[ra.b];
+      }
+    }
+    if (lane == 28) acc = (double)w_ties;
+    if (lane == 29) acc = (double)w_seed;
+    A.partials_main[(size_t)c * S2M_SUMS + lane] = acc;
+    __syncwarp();
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA: exclusive scan of the per-chunk leftover counts -> fail_off (chunk order) ----
+  __threadfence();
+  __shared__ int s_wsum[S2M_THREADS / 32];
+  __shared__ int s_carry;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nchunks; b0 += S2M_THREADS) {
+    const int b = b0 + tid;
+    const int cnt = b < nchunks ? __ldcg(A.block_nfail + b) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int base = s_carry;
+    for (int w = 0; w < warp; ++w) base += s_wsum[w];
+    if (b < nchunks) A.fail_off[b] = base + incl - cnt;
+    __syncthreads();
+    if (tid == S2M_THREADS - 1) s_carry = base + incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    A.fail_off[nchunks] = s_carry;
+    *A.fail_total = s_carry;
+    *A.ticket = 0u;
+    *A.queue = 0u;
+  }
+}
+
 constexpr int LEFT_THREADS = 256;
 __global__ void __launch_bounds__(LEFT_THREADS, 2)
 s2m_left_kernel(const S2mArgs A) {
@@ -1060,7 +1179,7 @@ s2m_left_kernel(const S2mArgs A) {
   if (tid == 64) { s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = *A.fail_total; }
   // the offsets of the per-block leftover segments, staged once: the binary search below then runs on
   // shared memory instead of ten dependent L2 round trips
-  constexpr int OFF_CAP = 4096;
+  constexpr int OFF_CAP = 8192;
   __shared__ int s_off[OFF_CAP];
   const bool off_in_smem = A.main_blocks + 1 <= OFF_CAP;
   if (off_in_smem)
@@ -1100,7 +1219,7 @@ s2m_left_kernel(const S2mArgs A) {
             const int v = off_in_smem ? s_off[mid] : __ldg(A.fail_off + mid);
             if (v <= e) lo = mid; else hi = mid;
           }
-          mine = A.fail_seg[(size_t)lo * S2M_THREADS + (e - (off_in_smem ? s_off[lo] : __ldg(A.fail_off + lo)))];
+          mine = A.fail_seg[(size_t)lo * A.seg_stride + (e - (off_in_smem ? s_off[lo] : __ldg(A.fail_off + lo)))];
         }
       }
       float4 ori = make_float4(0.f, 0.f, 0.f, 0.f), sel = ori;
@@ -1218,14 +1337,33 @@ static int check_grid(Ctx* c) {
 }
 
 // device scratch shared by both entry points
+// CTAs of the persistent-warp main kernel: every resident slot, but no more warps than chunks
+static int pw_grid_size(Ctx* c, int nchunks) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2m_main_pw_kernel, S2M_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  }
+  const int full = per_sm * c->sm_count;
+  const int need = div_up(nchunks, S2M_THREADS / 32);
+  return need < full ? (need > 0 ? need : 1) : full;
+}
+
+static bool use_pw_main(const Ctx* c) {
+  static const int env = [] { const char* e = getenv("LIOGPU_MAIN"); return e ? (!strcmp(e, "fixed") ? 0 : (!strcmp(e, "pw") ? 1 : -1)) : -1; }();
+  (void)c;
+  return env != 0;  // default: persistent warps; LIOGPU_MAIN=fixed selects round 1's fixed grid (A/B)
+}
+
 static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& main_blocks, int& left_blocks) {
-  main_blocks = div_up(n, S2M_THREADS);
+  const bool pw = use_pw_main(c);
+  main_blocks = pw ? div_up(n, 32) : div_up(n, S2M_THREADS);  // partial rows / leftover segments: per chunk or per block
   // two CTAs per SM: a leftover point is a serial chain of dependent look-ups (~5 us), so they are spread
   // over as many resident warps as possible (one point per warp up to 2368 points)
   left_blocks = c->sm_count * 2;
   LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
   LIOGPU_CUDA_OK(c, c->partials.reserve(((size_t)main_blocks + left_blocks) * S2M_SUMS * sizeof(double)));
-  LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)main_blocks * S2M_THREADS + 2 * (size_t)main_blocks + 64) * sizeof(int)));
+  const int seg = pw ? 32 : S2M_THREADS;
+  LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)main_blocks * seg + 2 * (size_t)main_blocks + 64) * sizeof(int)));
   if (!c->block_counter.p) {
     LIOGPU_CUDA_OK(c, c->block_counter.reserve(64));
     LIOGPU_CUDA_OK(c, cudaMemsetAsync(c->block_counter.p, 0, 64, c->stream));
@@ -1238,7 +1376,9 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   A.partials_left = A.partials_main + (size_t)main_blocks * S2M_SUMS;
   int* fb = c->fail_buf.as<int>();
   A.fail_seg = fb;
-  A.fail_off = fb + (size_t)main_blocks * S2M_THREADS;
+  A.seg_stride = seg;
+  A.queue = c->block_counter.as<unsigned>() + 4;
+  A.fail_off = fb + (size_t)main_blocks * seg;
   A.block_nfail = A.fail_off + main_blocks + 1;
   A.fail_total = A.block_nfail + main_blocks;
   A.ticket = c->block_counter.as<unsigned>();
@@ -1322,14 +1462,15 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
     LIOGPU_CUDA_OK(c, cudaMemsetAsync(A.probe, 0, LIOGPU_MAX_ITER * FZ_PROBES * sizeof(unsigned long long), c->stream));
   }
   LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
-  memset(h, 0, sizeof(LmDevState));
-  for (int k = 0; k < 6; ++k) h->pose[k] = pose_io[k];
-  for (int k = 0; k < 36; ++k) h->matP[k] = matP_io[k];
-  h->degenerate = *degenerate_io;
-  h->max_iter = max_iter;
+  LmInit init;
+  for (int k = 0; k < 6; ++k) init.pose[k] = pose_io[k];
+  for (int k = 0; k < 36; ++k) init.matP[k] = matP_io[k];
+  init.degenerate = *degenerate_io;
+  init.max_iter = max_iter;
   LmDevState* d = A.st;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+  lm_prepare_kernel<<<1, 256, 0, c->stream>>>(d, init);
+  c->launches++;
   void* kargs[] = {(void*)&A};
   LIOGPU_CUDA_OK(c, cudaLaunchCooperativeKernel((const void*)s2m_fused_kernel, dim3((unsigned)grid), dim3(FZ_THREADS), kargs, 0, c->stream));
   c->launches++;
@@ -1343,7 +1484,7 @@ static int scan2map_fused_dev(Ctx* c, const float4* scan4, int n, float pose_io[
   *degenerate_io = h->degenerate;
   if (info) {
     fill_info(c, h, n, info);
-    info->kernel_launches = 1;
+    info->kernel_launches = 1;  // the loop itself (plus the 2.5 KB state initialisation)
     for (int it = 0; it < LIOGPU_MAX_ITER; ++it) {
       info->certified_hist[it] = h->cert_hist[it]; info->seeded_hist[it] = h->seed_hist[it];
       info->leftover_hist[it] = h->left_hist[it];
@@ -1427,22 +1568,23 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
   rc = prepare_args(c, scan4, n, A, main_blocks, left_blocks);
   if (rc != LIOGPU_OK) return rc;
   LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
-  memset(h, 0, sizeof(LmDevState));
-  for (int k = 0; k < 6; ++k) h->pose[k] = pose_io[k];
-  for (int k = 0; k < 36; ++k) h->matP[k] = matP_io[k];
-  h->degenerate = *degenerate_io;
-  h->max_iter = max_iter;
+  LmInit init;
+  for (int k = 0; k < 6; ++k) init.pose[k] = pose_io[k];
+  for (int k = 0; k < 36; ++k) init.matP[k] = matP_io[k];
+  init.degenerate = *degenerate_io;
+  init.max_iter = max_iter;
   LmDevState* d = A.st;
   const unsigned long long launches_before = c->launches;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  lm_prepare_kernel<<<1, 32, 0, c->stream>>>(d);
+  lm_prepare_kernel<<<1, 256, 0, c->stream>>>(d, init);
   c->launches++;
   // The loop never waits for the host inside a chunk: S2M_CHUNK iterations are enqueued back to back
   // (a launch that finds `done` set exits at once), then the state block is read back — the same single
   // read-back a converged registration needs anyway.  Only scans that need more than S2M_CHUNK iterations
   // pay a second round trip.
   const int S2M_CHUNK = 5;
+  const bool pw = use_pw_main(c);
+  const int pw_grid = pw_grid_size(c, main_blocks);
   int launched = 0;
   float prof_main_ms = 0.f, prof_left_ms = 0.f;
   int prof_main_n = 0, prof_left_n = 0;
@@ -1459,7 +1601,10 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
     for (int it = 0; it < todo; ++it) {
       const bool first = launched + it == 0;
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
-      if (two_phase || !first) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
+      if (two_phase || !first) {
+        if (pw) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_pw_kernel, pw_grid, S2M_THREADS, c->stream, A));
+        else LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
+      }
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
       LIOGPU_CUDA_OK(c, launch_pdl(s2m_left_kernel, left_blocks, LEFT_THREADS, c->stream, A));
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 2], c->stream));
@@ -1519,12 +1664,11 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
   LIOGPU_CUDA_OK(c, c->dbg_coeff.reserve((size_t)n * sizeof(float4)));
   LIOGPU_CUDA_OK(c, c->dbg_flag.reserve((size_t)n));
   LIOGPU_CUDA_OK(c, c->dbg_tie.reserve((size_t)n));
-  LmDevState* h = reinterpret_cast<LmDevState*>((char*)c->h_pinned + 4096);
-  memset(h, 0, sizeof(LmDevState));
-  if (pose6) for (int k = 0; k < 6; ++k) h->pose[k] = pose6[k];
+  LmInit init;
+  memset(&init, 0, sizeof(init));
+  if (pose6) for (int k = 0; k < 6; ++k) init.pose[k] = pose6[k];
   LmDevState* d = A.st;
-  LIOGPU_CUDA_OK(c, cudaMemcpyAsync(d, h, sizeof(LmDevState), cudaMemcpyHostToDevice, c->stream));
-  lm_prepare_kernel<<<1, 32, 0, c->stream>>>(d);
+  lm_prepare_kernel<<<1, 256, 0, c->stream>>>(d, init);
   c->launches++;
   if (T12) {
     float* d_T = c->misc.as<float>() + 16;
@@ -1537,7 +1681,10 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
                        c->dbg_flag.as<unsigned char>(), c->dbg_tie.as<unsigned char>()};
   A.mode = 1;
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
-  if (A.g.gate1_d2 < A.g.gate_d2) s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+  if (A.g.gate1_d2 < A.g.gate_d2) {
+    if (use_pw_main(c)) s2m_main_pw_kernel<<<pw_grid_size(c, main_blocks), S2M_THREADS, 0, c->stream>>>(A);
+    else s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+  }
   s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
   c->launches += 2;
   LIOGPU_CUDA_OK(c, cudaGetLastError());
