@@ -1062,7 +1062,8 @@ s2m_main_kernel(const S2mArgs A) {
 
 // Persistent-warp variant of s2m_main_kernel (round 2, VERDICT lever (i)): the grid is sized to residency and every
 // WARP pulls 32-point chunks from an atomic queue until the sweep is exhausted, so no SM idles while work remains (the
-// fixed grid left 23 % of the SM-cycles idle: 900 CTAs on 592 slots).  A chunk's 27 sums go to its own partial row and
+// fixed grid leaves 23 % of the SM-cycles idle: 900 CTAs on 592 slots).  MEASURED SLOWER than the fixed grid (config 3:
+// 88 vs 78 us per launch; 16-beam shape 21 vs 20): kept for A/B (LIOGPU_MAIN=pw), not the default.  A chunk's 27 sums go to its own partial row and
 // its leftovers to its own segment (both indexed by the chunk, so the result does not depend on which warp took it);
 // the last CTA to finish turns the per-chunk leftover counts into offsets, exactly as the fixed-grid kernel does per block.
 __global__ void __launch_bounds__(S2M_THREADS, S2M_MINBLOCKS_CFG)
@@ -1351,7 +1352,8 @@ static int pw_grid_size(Ctx* c, int nchunks) {
 static bool use_pw_main(const Ctx* c) {
   static const int env = [] { const char* e = getenv("LIOGPU_MAIN"); return e ? (!strcmp(e, "fixed") ? 0 : (!strcmp(e, "pw") ? 1 : -1)) : -1; }();
   (void)c;
-  return env != 0;  // default: persistent warps; LIOGPU_MAIN=fixed selects round 1's fixed grid (A/B)
+  return env == 1;  // default: the fixed grid (measured faster: 104 vs 117 us per iteration on config 3); LIOGPU_MAIN=pw
+                    // selects the persistent-warp kernel for A/B runs
 }
 
 static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& main_blocks, int& left_blocks) {
