@@ -1282,19 +1282,33 @@ s2m_left_kernel(const S2mArgs A) {
   if (!s_last) return;
   __threadfence();
   {  // fixed-order sum over the left blocks: 8 slices of blocks, then the slices
-    // four independent accumulators: the loads of a group are in flight together (fixed order of additions)
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    constexpr unsigned W = LEFT_THREADS / 32;
+    // sixteen independent accumulators: the pass is L2-latency bound, so the loads of a group are all in flight together
+    // (fixed order of additions: accumulator k takes blocks warp + (16 j + k) W, then the accumulators are added pairwise)
+    constexpr unsigned W = LEFT_THREADS / 32, U = 16;
+    double a[U];
+#pragma unroll
+    for (unsigned k = 0; k < U; ++k) a[k] = 0.0;
     unsigned b = warp;
-    for (; b + 3 * W < gridDim.x; b += 4 * W) {
-      const double v0 = __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
-      const double v1 = __ldcg(A.partials_left + (size_t)(b + W) * S2M_SUMS + lane);
-      const double v2 = __ldcg(A.partials_left + (size_t)(b + 2 * W) * S2M_SUMS + lane);
-      const double v3 = __ldcg(A.partials_left + (size_t)(b + 3 * W) * S2M_SUMS + lane);
-      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    for (; b + (U - 1) * W < gridDim.x; b += U * W) {
+      double v[U];
+#pragma unroll
+      for (unsigned k = 0; k < U; ++k) v[k] = __ldcg(A.partials_left + (size_t)(b + k * W) * S2M_SUMS + lane);
+#pragma unroll
+      for (unsigned k = 0; k < U; ++k) a[k] += v[k];
     }
-    for (; b < gridDim.x; b += W) a0 += __ldcg(A.partials_left + (size_t)b * S2M_SUMS + lane);
-    red[warp][lane] = (a0 + a1) + (a2 + a3);
+    {
+      double v[U];
+#pragma unroll
+      for (unsigned k = 0; k < U; ++k) v[k] = (b + k * W < gridDim.x) ? __ldcg(A.partials_left + (size_t)(b + k * W) * S2M_SUMS + lane) : 0.0;
+#pragma unroll
+      for (unsigned k = 0; k < U; ++k) a[k] += v[k];
+    }
+#pragma unroll
+    for (unsigned o = U / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (unsigned k = 0; k < o; ++k) a[k] += a[k + o];
+    }
+    red[warp][lane] = a[0];
   }
   __syncthreads();
   if (tid < S2M_SUMS) {
