@@ -270,7 +270,15 @@ os_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
       key[it] = keys_in[idx];
       val[it] = vals_in ? vals_in[idx] : (uint32_t)idx;
       const uint32_t d = (key[it] >> shift) & 255u;
-      const unsigned peers = __match_any_sync(act, d);
+      // lanes holding the same digit: eight ballots (one per digit bit) instead of match_any, whose cost grows with the
+      // number of distinct values in the warp (≈30 for random digits)
+      unsigned peers = act;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(act, bit);
+        peers &= bit ? m : ~m;
+      }
       const uint32_t pre = warp_hist[w][d];
       __syncwarp(act);
       if ((peers & lt_mask) == 0) warp_hist[w][d] = pre + __popc(peers);
