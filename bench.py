@@ -345,6 +345,10 @@ def bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank
     tile_ms, plan_ms, gather_ms, wall_ms = [], [], [], []
     n_mine = 0
     gathered = None
+    tile_cap = int(n_ref)   # no tile holds more voxels than the whole map
+    my_size = torch.zeros(1, dtype=torch.int32, device=dev)
+    sizes_all = torch.zeros(world_size, dtype=torch.int32, device=dev)
+    gbuf = torch.empty((world_size * tile_cap, 4), dtype=torch.float32, device=dev)
     for s in range(steps + 2):
         torch.cuda.synchronize()
         if dist is not None:
@@ -354,14 +358,13 @@ def bench_cfg4(torch, dist, LioGpu, default_params, rank, world_size, local_rank
         n_mine, inf, st = g.voxel_tile(ids, poses, leaf, rank, world_size, out=(mine.data_ptr(), cap))
         t1 = time.perf_counter()
         if dist is not None:
-            # ordered gather of the tiles: sizes first (8 x int32), then the padded tiles over NVLink / NVSwitch
-            sizes = torch.zeros(world_size, dtype=torch.int32, device=dev)
-            sizes[rank] = n_mine
-            dist.all_reduce(sizes)
-            mx = int(sizes.max().item())
-            bufs = [torch.empty((mx, 4), dtype=torch.float32, device=dev) for _ in range(world_size)]
-            dist.all_gather(bufs, mine[:mx].contiguous())
-            gathered = torch.cat([bufs[r][: int(sizes[r].item())] for r in range(world_size)])
+            # ordered gather of the tiles over NVLink / NVSwitch: two collectives (sizes, fixed-capacity tiles), one host
+            # read-back of the sizes, then the slices are concatenated in rank order on the device
+            my_size[0] = n_mine
+            dist.all_gather_into_tensor(sizes_all, my_size)
+            dist.all_gather_into_tensor(gbuf, mine[:tile_cap])
+            sz = sizes_all.tolist()
+            gathered = torch.cat([gbuf[r * tile_cap: r * tile_cap + sz[r]] for r in range(world_size)])
             torch.cuda.synchronize()
         else:
             gathered = mine[:n_mine]

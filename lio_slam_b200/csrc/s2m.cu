@@ -39,6 +39,10 @@ namespace liogpu {
 #define S2M_MINBLOCKS_CFG 4
 #endif
 constexpr int S2M_THREADS = S2M_THREADS_CFG;
+// The leftover kernel turns the main kernel's per-block (per-chunk) leftover counts into segment offsets itself, in
+// shared memory, when the table fits; the main kernels then end without a ticket and without the serial scan their last
+// block used to run (4 rounds on the fixed grid, 29 on the per-chunk table of the persistent-warp kernel).
+constexpr int LEFT_OFF_CAP = 8192;
 constexpr int S2M_SUMS = 32;  // 21 (upper AtA) + 6 (AtB) + nsel + ties, padded to 32
 
 struct SurfDebugOut {
@@ -75,6 +79,23 @@ struct Top5 {
       rej = fminf(rej, d);
     }
   }
+  // The list already holds real map points (the previous iteration's neighbours): a candidate that IS one of them is
+  // skipped — it neither enters twice nor counts as a rejected candidate.
+  __device__ __forceinline__ void offer_seeded(float d, int id) {
+    const u64 key = (((u64)__float_as_uint(d)) << 32) | (u64)(unsigned)id;
+    if (key < k4) {
+      if (key == k0 || key == k1 || key == k2 || key == k3) return;
+      rej = fminf(rej, __uint_as_float((unsigned)(k4 >> 32)));
+      u64 lo;
+      k4 = key;
+      lo = min(k3, k4); k4 = max(k3, k4); k3 = lo;
+      lo = min(k2, k3); k3 = max(k2, k3); k2 = lo;
+      lo = min(k1, k2); k2 = max(k1, k2); k1 = lo;
+      lo = min(k0, k1); k1 = max(k0, k1); k0 = lo;
+    } else if (key != k4) {
+      rej = fminf(rej, d);
+    }
+  }
   __device__ __forceinline__ float d(const u64 k) const { return __uint_as_float((unsigned)(k >> 32)); }
   __device__ __forceinline__ int i(const u64 k) const { return (int)(unsigned)(k & 0xffffffffull); }
   __device__ __forceinline__ bool tie() const {
@@ -95,10 +116,12 @@ __device__ __forceinline__ int zigzag(int k) { return (k & 1) ? -((k + 1) >> 1) 
 
 // Exact 5 nearest map points of q among those closer than sqrt(gate_d2), ascending (d2, map index).
 // On return t.d(t.k4) < gate_d2 iff at least 5 such points exist (then the answer is exact).
+// PRESET: t already holds five real map points closer than sqrt(gate_d2) (in order); the walk skips them when it meets them.
+template <bool PRESET = false>
 __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, const float gate_d2,
                                           const float4* __restrict__ map_sorted,
                                           const uint32_t* __restrict__ cell_start, Top5& t) {
-  t.init(gate_d2);
+  if (!PRESET) t.init(gate_d2);
   const float s2 = 2.0f * g.slack;
   const float reach = sqrtf(gate_d2) * 1.000001f + s2;
   int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
@@ -142,10 +165,17 @@ __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, c
         const float4 p1 = __ldg(map_sorted + min(j + 1, last));
         const float4 p2 = __ldg(map_sorted + min(j + 2, last));
         const float4 p3 = __ldg(map_sorted + min(j + 3, last));
-        t.offer(l2_simple(q, p0), __float_as_int(p0.w));
-        if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
-        if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
-        if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
+        if (PRESET) {
+          t.offer_seeded(l2_simple(q, p0), __float_as_int(p0.w));
+          if (j + 1 < e) t.offer_seeded(l2_simple(q, p1), __float_as_int(p1.w));
+          if (j + 2 < e) t.offer_seeded(l2_simple(q, p2), __float_as_int(p2.w));
+          if (j + 3 < e) t.offer_seeded(l2_simple(q, p3), __float_as_int(p3.w));
+        } else {
+          t.offer(l2_simple(q, p0), __float_as_int(p0.w));
+          if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
+          if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
+          if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
+        }
       }
     }
   }
@@ -157,10 +187,11 @@ __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, c
 // and the rows are then walked centre-out with the usual pruning against the running 5th-best distance.
 // The x range of a row is fixed from the initial bound (a superset of what the tightened bound would give);
 // the extra candidates cost one compare each.  Returns false when the box is larger (caller falls back).
+template <bool PRESET = false>
 __device__ __forceinline__ bool grid_knn5_box9(const float4 q, const GridParams& g, const float gate_d2,
                                                const float4* __restrict__ map_sorted,
                                                const uint32_t* __restrict__ cell_start, Top5& t) {
-  t.init(gate_d2);
+  if (!PRESET) t.init(gate_d2);
   const float s2 = 2.0f * g.slack;
   const float reach = sqrtf(gate_d2) * 1.000001f + s2;
   int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
@@ -211,10 +242,17 @@ __device__ __forceinline__ bool grid_knn5_box9(const float4 q, const GridParams&
       const float4 p1 = __ldg(map_sorted + min(j + 1, last));
       const float4 p2 = __ldg(map_sorted + min(j + 2, last));
       const float4 p3 = __ldg(map_sorted + min(j + 3, last));
-      t.offer(l2_simple(q, p0), __float_as_int(p0.w));
-      if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
-      if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
-      if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
+      if (PRESET) {
+        t.offer_seeded(l2_simple(q, p0), __float_as_int(p0.w));
+        if (j + 1 < e) t.offer_seeded(l2_simple(q, p1), __float_as_int(p1.w));
+        if (j + 2 < e) t.offer_seeded(l2_simple(q, p2), __float_as_int(p2.w));
+        if (j + 3 < e) t.offer_seeded(l2_simple(q, p3), __float_as_int(p3.w));
+      } else {
+        t.offer(l2_simple(q, p0), __float_as_int(p0.w));
+        if (j + 1 < e) t.offer(l2_simple(q, p1), __float_as_int(p1.w));
+        if (j + 2 < e) t.offer(l2_simple(q, p2), __float_as_int(p2.w));
+        if (j + 3 < e) t.offer(l2_simple(q, p3), __float_as_int(p3.w));
+      }
     }
   }
   return true;
@@ -824,7 +862,8 @@ struct S2mArgs {
   const float* T_override;
   SurfDebugOut dbg;
   int mode;
-  int main_blocks;
+  int main_blocks;         // partial rows of the main phase
+  int seg_blocks;          // leftover segments (= main_blocks except for the split search kernel's smaller blocks)
   int seg_stride;          // slots per segment of fail_seg (S2M_THREADS, or 32 for the persistent-warp main kernel)
   unsigned* queue;         // chunk queue head of the persistent-warp main kernel
   int* prev_nn;            // [5][nq] neighbours found by the previous iteration (-1: none), SoA
@@ -913,17 +952,23 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
       if (p0 >= 0) {
         const int p1 = A.prev_nn[(size_t)A.nq + i], p2 = A.prev_nn[2 * (size_t)A.nq + i];
         const int p3 = A.prev_nn[3 * (size_t)A.nq + i], p4 = A.prev_nn[4 * (size_t)A.nq + i];
-        float D = l2_simple(sel, __ldg(A.map4 + p0));
-        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p1)));
-        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p2)));
-        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p3)));
-        D = fmaxf(D, l2_simple(sel, __ldg(A.map4 + p4)));
+        const float d0 = l2_simple(sel, __ldg(A.map4 + p0)), d1 = l2_simple(sel, __ldg(A.map4 + p1));
+        const float d2 = l2_simple(sel, __ldg(A.map4 + p2)), d3 = l2_simple(sel, __ldg(A.map4 + p3));
+        const float d4 = l2_simple(sel, __ldg(A.map4 + p4));
+        const float D = fmaxf(fmaxf(fmaxf(d0, d1), fmaxf(d2, d3)), d4);
         const float bound = __uint_as_float(__float_as_uint(D) + 1u);  // next float above D: the seeds stay inside
         if (bound <= A.g.gate_d2) {
           gate_use = bound;
           can_search = true;
           is_seeded = true;
           ++seeded;
+#ifndef S2M_NO_SEED_INIT
+          // The five seeds enter the list up front, all lanes together.  In a late iteration they ARE the answer and the
+          // walk then inserts nothing: the insertion network otherwise runs ~30 times per warp at 5 of 32 lanes (25 % of
+          // the kernel's instructions, profiles/r02_ncu_source_hotspots_*).  Measured: -8 us per seeded launch.
+          t.init(bound);
+          t.offer(d0, p0); t.offer(d1, p1); t.offer(d2, p2); t.offer(d3, p3); t.offer(d4, p4);
+#endif
         }
       }
     }
@@ -936,6 +981,12 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
       // and the kernel is issue bound; sparse map (1 m cells, few points per row): the search is latency
       // bound and the all-rows-at-once variant wins
       const bool sparse = !(A.g.gate1_d2 < A.g.gate_d2);
+#ifndef S2M_NO_SEED_INIT
+      if (is_seeded) {
+        if (!sparse || !grid_knn5_box9<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
+          grid_knn5<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+      } else
+#endif
       if (!sparse || !grid_knn5_box9(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
 #endif
         grid_knn5(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
@@ -1024,6 +1075,7 @@ s2m_main_kernel(const S2mArgs A) {
     for (int w = 0; w < S2M_THREADS / 32; ++w) nf += s_wfail[w];
     A.block_nfail[blockIdx.x] = nf;
   }
+  if (A.seg_blocks + 1 <= LEFT_OFF_CAP) return;  // the leftover kernel derives the offsets itself
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
@@ -1119,6 +1171,7 @@ s2m_main_pw_kernel(const S2mArgs A) {
     A.partials_main[(size_t)c * S2M_SUMS + lane] = acc;
     __syncwarp();
   }
+  if (nchunks + 1 <= LEFT_OFF_CAP) return;  // offsets: leftover kernel; queue head: reset there too
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
@@ -1177,14 +1230,34 @@ s2m_left_kernel(const S2mArgs A) {
     sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
     s_ties = 0;
   }
-  if (tid == 64) { s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = *A.fail_total; }
-  // the offsets of the per-block leftover segments, staged once: the binary search below then runs on
-  // shared memory instead of ten dependent L2 round trips
-  constexpr int OFF_CAP = 8192;
-  __shared__ int s_off[OFF_CAP];
-  const bool off_in_smem = A.main_blocks + 1 <= OFF_CAP;
-  if (off_in_smem)
-    for (int k = tid; k <= A.main_blocks; k += LEFT_THREADS) s_off[k] = A.fail_off[k];
+  const bool off_in_smem = A.seg_blocks + 1 <= LEFT_OFF_CAP;
+  if (tid == 64) { s_done0 = A.st->done; s_iter0 = A.st->iter; s_total0 = off_in_smem ? 0 : *A.fail_total; }
+  if (tid == 96 && blockIdx.x == 0) *A.queue = 0u;  // chunk queue of the persistent-warp main kernel
+  // The offsets of the leftover segments (exclusive scan of the main kernel's per-block counts), computed HERE by every
+  // block in shared memory: every thread sums a contiguous slice of the counts (all loads in flight), one block-wide scan
+  // of the 256 slice sums, then the slice's prefixes are written out.  The binary search below runs on shared memory.
+  __shared__ int s_off[LEFT_OFF_CAP];
+  __shared__ int s_wsum[LEFT_THREADS / 32];
+  if (off_in_smem) {
+    for (int k = tid; k < A.seg_blocks; k += LEFT_THREADS) s_off[k] = __ldcg(A.block_nfail + k);  // one round trip
+    __syncthreads();
+    const int per = (A.seg_blocks + LEFT_THREADS - 1) / LEFT_THREADS;
+    const int k0 = min(tid * per, A.seg_blocks), k1 = min(k0 + per, A.seg_blocks);
+    int sum = 0;
+    for (int k = k0; k < k1; ++k) sum += s_off[k];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int run = incl - sum;
+    for (int w = 0; w < warp; ++w) run += s_wsum[w];
+    for (int k = k0; k < k1; ++k) { const int v = s_off[k]; s_off[k] = run; run += v; }
+    if (tid == LEFT_THREADS - 1) { s_off[A.seg_blocks] = run; s_total0 = run; }
+  }
   __syncthreads();
   if (A.mode == 0 && s_done0) return;
   // sparse map (no phase-1 gate): on iteration 0 (and in mode 1) the main kernel did not run at all
@@ -1214,7 +1287,7 @@ s2m_left_kernel(const S2mArgs A) {
         if (all_points) {
           mine = e;
         } else {  // leftover e lives in the segment of the main block whose offset range contains it
-          int lo = 0, hi = A.main_blocks;  // invariant: fail_off[lo] <= e < fail_off[hi]
+          int lo = 0, hi = A.seg_blocks;  // invariant: fail_off[lo] <= e < fail_off[hi]
           while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             const int v = off_in_smem ? s_off[mid] : __ldg(A.fail_off + mid);
@@ -1325,6 +1398,8 @@ s2m_left_kernel(const S2mArgs A) {
 }
 
 }  // namespace liogpu
+#include "s2m_wc.cuh"
+#include "s2m_split.cuh"
 #include "s2m_fused.cuh"
 namespace liogpu {
 
@@ -1332,11 +1407,11 @@ namespace liogpu {
 // as the previous one drains (its last block is still reducing / solving the 6x6 system) and waits in
 // cudaGridDependencySynchronize(), which hides the launch latency between dependent kernels.
 template <class K>
-static cudaError_t launch_pdl(K kernel, int blocks, int threads, cudaStream_t stream, const S2mArgs& A) {
+static cudaError_t launch_pdl(K kernel, int blocks, int threads, cudaStream_t stream, const S2mArgs& A, size_t smem = 0) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)blocks);
   cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1363,23 +1438,54 @@ static int pw_grid_size(Ctx* c, int nchunks) {
   return need < full ? (need > 0 ? need : 1) : full;
 }
 
+// LIOGPU_MAIN = fixed | pw | wc | wc1 | split selects the main kernel for A/B runs: the thread-per-point walk on a fixed grid, the
+// same on persistent warps, the warp-cooperative candidate evaluation (s2m_wc.cuh) for every iteration, or for the
+// seeded iterations only (iteration 0 on the fixed grid).
+static int main_variant_env() {
+  static const int env = [] {
+    const char* e = getenv("LIOGPU_MAIN");
+    if (!e) return -1;
+    if (!strcmp(e, "fixed")) return 0;
+    if (!strcmp(e, "pw")) return 1;
+    if (!strcmp(e, "wc")) return 2;
+    if (!strcmp(e, "wc1")) return 3;
+    if (!strcmp(e, "split")) return 4;
+    return -1;
+  }();
+  return env;
+}
 static bool use_pw_main(const Ctx* c) {
-  static const int env = [] { const char* e = getenv("LIOGPU_MAIN"); return e ? (!strcmp(e, "fixed") ? 0 : (!strcmp(e, "pw") ? 1 : -1)) : -1; }();
   (void)c;
-  return env == 1;  // default: the fixed grid (measured faster: 104 vs 117 us per iteration on config 3); LIOGPU_MAIN=pw
-                    // selects the persistent-warp kernel for A/B runs
+  return main_variant_env() == 1;  // the fixed grid measured faster than persistent warps (104 vs 117 us per iteration, config 3)
+}
+// the warp-cooperative kernel needs the dense-map grid (cell edge = phase-1 radius: a ball touches at most 3 x 3 rows)
+static bool use_wc_main(const Ctx* c, bool first_iteration) {
+  const int v = main_variant_env();
+  if (!(c->grid.gate1_d2 < c->grid.gate_d2)) return false;
+  return v == 2 || (v == 3 && !first_iteration);
+}
+// the split path packs two flag bits into a neighbour index and lets the leftover kernel scan the per-block leftover counts
+// in shared memory: maps below 2^29 points, sweeps below 64 x 8191 points, dense-map grid
+static bool use_split_main(const Ctx* c, int n) {
+  return main_variant_env() == 4 && c->n_map < (1 << 29) && div_up(n, SEARCH_THREADS) + 1 <= LEFT_OFF_CAP;
+}
+static cudaError_t wc_prepare() {
+  static const cudaError_t rc = cudaFuncSetAttribute(s2m_main_wc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WC_SMEM_BYTES);
+  return rc;
 }
 
 static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& main_blocks, int& left_blocks) {
   const bool pw = use_pw_main(c);
-  main_blocks = pw ? div_up(n, 32) : div_up(n, S2M_THREADS);  // partial rows / leftover segments: per chunk or per block
+  const bool split = use_split_main(c, n);
+  main_blocks = pw ? div_up(n, 32) : div_up(n, S2M_THREADS);  // partial rows: per chunk or per block
+  const int seg = pw ? 32 : (split ? SEARCH_THREADS : S2M_THREADS);  // leftover segments: per chunk / search block / block
+  const int seg_blocks = div_up(n, seg);
   // two CTAs per SM: a leftover point is a serial chain of dependent look-ups (~5 us), so they are spread
   // over as many resident warps as possible (one point per warp up to 2368 points)
   left_blocks = c->sm_count * 2;
   LIOGPU_CUDA_OK(c, c->lm_state.reserve(sizeof(LmDevState)));
   LIOGPU_CUDA_OK(c, c->partials.reserve(((size_t)main_blocks + left_blocks) * S2M_SUMS * sizeof(double)));
-  const int seg = pw ? 32 : S2M_THREADS;
-  LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)main_blocks * seg + 2 * (size_t)main_blocks + 64) * sizeof(int)));
+  LIOGPU_CUDA_OK(c, c->fail_buf.reserve(((size_t)seg_blocks * seg + 2 * (size_t)seg_blocks + 64) * sizeof(int)));
   if (!c->block_counter.p) {
     LIOGPU_CUDA_OK(c, c->block_counter.reserve(64));
     LIOGPU_CUDA_OK(c, cudaMemsetAsync(c->block_counter.p, 0, 64, c->stream));
@@ -1393,10 +1499,11 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   int* fb = c->fail_buf.as<int>();
   A.fail_seg = fb;
   A.seg_stride = seg;
+  A.seg_blocks = seg_blocks;
   A.queue = c->block_counter.as<unsigned>() + 4;
-  A.fail_off = fb + (size_t)main_blocks * seg;
-  A.block_nfail = A.fail_off + main_blocks + 1;
-  A.fail_total = A.block_nfail + main_blocks;
+  A.fail_off = fb + (size_t)seg_blocks * seg;
+  A.block_nfail = A.fail_off + seg_blocks + 1;
+  A.fail_total = A.block_nfail + seg_blocks;
   A.ticket = c->block_counter.as<unsigned>();
   LIOGPU_CUDA_OK(c, c->prev_nn.reserve((size_t)5 * (size_t)(n > 0 ? n : 1) * sizeof(int)));
   A.prev_nn = c->prev_nn.as<int>();
@@ -1601,6 +1708,7 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
   const int S2M_CHUNK = 5;
   const bool pw = use_pw_main(c);
   const int pw_grid = pw_grid_size(c, main_blocks);
+  LIOGPU_CUDA_OK(c, wc_prepare());
   int launched = 0;
   float prof_main_ms = 0.f, prof_left_ms = 0.f;
   int prof_main_n = 0, prof_left_n = 0;
@@ -1619,6 +1727,11 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it], c->stream));
       if (two_phase || !first) {
         if (pw) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_pw_kernel, pw_grid, S2M_THREADS, c->stream, A));
+        else if (use_split_main(c, n)) {
+          LIOGPU_CUDA_OK(c, launch_pdl(s2m_search_kernel, A.seg_blocks, SEARCH_THREADS, c->stream, A));
+          LIOGPU_CUDA_OK(c, launch_pdl(s2m_fit_kernel, main_blocks, S2M_THREADS, c->stream, A));
+          c->launches++;
+        } else if (use_wc_main(c, first)) LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_wc_kernel, main_blocks, S2M_THREADS, c->stream, A, WC_SMEM_BYTES));
         else LIOGPU_CUDA_OK(c, launch_pdl(s2m_main_kernel, main_blocks, S2M_THREADS, c->stream, A));
       }
       if (prof) LIOGPU_CUDA_OK(c, cudaEventRecord(c->prof_ev[3 * it + 1], c->stream));
@@ -1647,6 +1760,10 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
         cudaEventElapsedTime(&b, c->prof_ev[3 * it + 1], c->prof_ev[3 * it + 2]);
         if (two_phase || it > 0) { prof_main_ms += a; ++prof_main_n; }
         prof_left_ms += b; ++prof_left_n;
+        if (info && launched - todo + it < LIOGPU_MAX_ITER) {
+          info->main_us_hist[launched - todo + it] = a * 1e3f;
+          info->rest_us_hist[launched - todo + it] = b * 1e3f;
+        }
       }
     }
     if (h->done || launched >= max_iter) break;
@@ -1699,7 +1816,14 @@ int surf_optimization_dev(Ctx* c, const float4* scan4, int n, const float* pose6
   LIOGPU_CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
   if (A.g.gate1_d2 < A.g.gate_d2) {
     if (use_pw_main(c)) s2m_main_pw_kernel<<<pw_grid_size(c, main_blocks), S2M_THREADS, 0, c->stream>>>(A);
-    else s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+    else if (use_split_main(c, n)) {
+      s2m_search_kernel<<<A.seg_blocks, SEARCH_THREADS, 0, c->stream>>>(A);
+      s2m_fit_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
+      c->launches++;
+    } else if (use_wc_main(c, false)) {
+      LIOGPU_CUDA_OK(c, wc_prepare());
+      s2m_main_wc_kernel<<<main_blocks, S2M_THREADS, WC_SMEM_BYTES, c->stream>>>(A);
+    } else s2m_main_kernel<<<main_blocks, S2M_THREADS, 0, c->stream>>>(A);
   }
   s2m_left_kernel<<<left_blocks, LEFT_THREADS, 0, c->stream>>>(A);
   c->launches += 2;
