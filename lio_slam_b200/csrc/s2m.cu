@@ -181,6 +181,71 @@ __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, c
   }
 }
 
+// Collect variant of the walk for a TIGHT bound (a late seeded iteration: the bound is the previous neighbours' largest
+// distance to the barely moved point, i.e. already the answer's 5th distance): every candidate closer than the bound is
+// appended to the thread's list in shared memory by a few predicated instructions — no top-5 insertion inside the walk,
+// where it runs ~30 times per warp at 5 of 32 lanes; the five are selected afterwards with all lanes in step.  The bound
+// is not tightened during the walk (nothing to gain when it is tight from the start).  Returns the number of candidates
+// inside the bound; more than S2M_COLLECT_CAP means the list overflowed (the caller repeats with the insertion walk).
+#ifndef S2M_COLLECT_CAP_CFG
+#define S2M_COLLECT_CAP_CFG 16
+#endif
+constexpr int S2M_COLLECT_CAP = S2M_COLLECT_CAP_CFG;
+// When is a seeded bound tight?  When the point has barely moved since its neighbours were found.  The last pose
+// increment (deltaR in degrees, deltaT in cm: mapOptmization.cpp:1826-1833, kept in LmDevState) bounds that move by
+// deltaT + deltaR x range; a warp collects when at least three quarters of its seeded lanes moved less than this.
+#ifndef S2M_COLLECT_MOVE_CFG
+#define S2M_COLLECT_MOVE_CFG 0.20f
+#endif
+constexpr float S2M_COLLECT_MOVE = S2M_COLLECT_MOVE_CFG;  // metres
+template <int STRIDE>
+__device__ __forceinline__ int grid_knn5_collect(const float4 q, const GridParams& g, const float bound,
+                                                 const float4* __restrict__ map_sorted,
+                                                 const uint32_t* __restrict__ cell_start, u64* __restrict__ list) {
+  int cnt = 0;
+  const float s2 = 2.0f * g.slack;
+  const float reach = sqrtf(bound) * 1.000001f + s2;
+  int zmin = (int)floorf((q.z - reach - g.oz) * g.inv_h), zmax = (int)floorf((q.z + reach - g.oz) * g.inv_h);
+  int ymin = (int)floorf((q.y - reach - g.oy) * g.inv_h), ymax = (int)floorf((q.y + reach - g.oy) * g.inv_h);
+  zmin = max(zmin, 0); zmax = min(zmax, g.nz - 1);
+  ymin = max(ymin, 0); ymax = min(ymax, g.ny - 1);
+  for (int z = zmin; z <= zmax; ++z) {
+    const float zlo = g.oz + (float)z * g.h;
+    const float gz = fmaxf(fmaxf(zlo - q.z, q.z - (zlo + g.h)) - s2, 0.f);
+    const float gz2 = gz * gz;
+    if (gz2 > bound) continue;
+    for (int y = ymin; y <= ymax; ++y) {
+      const float ylo = g.oy + (float)y * g.h;
+      const float gy = fmaxf(fmaxf(ylo - q.y, q.y - (ylo + g.h)) - s2, 0.f);
+      const float m2 = (gz2 + gy * gy) * 0.999999f;
+      if (m2 > bound) continue;
+      const float r = sqrtf(bound - m2) * 1.000001f + s2;
+      int xlo = (int)floorf((q.x - r - g.ox) * g.inv_h);
+      int xhi = (int)floorf((q.x + r - g.ox) * g.inv_h);
+      xlo = max(xlo, 0);
+      xhi = min(xhi, g.nx - 1);
+      if (xlo > xhi) continue;
+      const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+      const uint32_t s = __ldg(cell_start + row + xlo);
+      const uint32_t e = __ldg(cell_start + row + xhi + 1);
+      // (issuing the next row's look-ups before this row's candidates are evaluated was measured: no change)
+      for (uint32_t j = s; j < e; j += 4) {
+        const uint32_t last = e - 1;
+        const float4 p0 = __ldg(map_sorted + j);
+        const float4 p1 = __ldg(map_sorted + min(j + 1, last));
+        const float4 p2 = __ldg(map_sorted + min(j + 2, last));
+        const float4 p3 = __ldg(map_sorted + min(j + 3, last));
+        const float d0 = l2_simple(q, p0), d1 = l2_simple(q, p1), d2 = l2_simple(q, p2), d3 = l2_simple(q, p3);
+        if (d0 < bound) { list[min(cnt, S2M_COLLECT_CAP - 1) * STRIDE] = (((u64)__float_as_uint(d0)) << 32) | (u64)__float_as_uint(p0.w); ++cnt; }
+        if ((j + 1 < e) & (d1 < bound)) { list[min(cnt, S2M_COLLECT_CAP - 1) * STRIDE] = (((u64)__float_as_uint(d1)) << 32) | (u64)__float_as_uint(p1.w); ++cnt; }
+        if ((j + 2 < e) & (d2 < bound)) { list[min(cnt, S2M_COLLECT_CAP - 1) * STRIDE] = (((u64)__float_as_uint(d2)) << 32) | (u64)__float_as_uint(p2.w); ++cnt; }
+        if ((j + 3 < e) & (d3 < bound)) { list[min(cnt, S2M_COLLECT_CAP - 1) * STRIDE] = (((u64)__float_as_uint(d3)) << 32) | (u64)__float_as_uint(p3.w); ++cnt; }
+      }
+    }
+  }
+  return cnt;
+}
+
 // Fast path of the per-thread search when the reach box covers at most 3 x 3 rows of cells (always the case
 // for the phase-1 gate and for a seeded search on a grid whose cell edge is the phase-1 radius): the
 // cell_start look-ups of ALL rows are issued together — one memory round trip instead of one per visited row —
@@ -931,12 +996,18 @@ __device__ __forceinline__ void finish_point(const S2mArgs& A, const int i, cons
 // One sweep point of surfOptimization: transform, exact search (phase-1 gate, seeded bound or skip), plane fit, Jacobian row.
 // need2: the phase-1 gate could not settle the point (it goes to the leftover list).
 __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, const LmTrig& sTrig, const int s_iter, const int i,
-                                           float row[6], float& rhs, bool& flag, bool& tie, bool& need2, int& seeded) {
+                                           float row[6], float& rhs, bool& flag, bool& tie, bool& need2, int& seeded,
+                                           u64* __restrict__ slist, const float step_t, const float step_r) {
     const float4 ori = A.scan[i];
     const float4 sel = apply_T(sT, ori);
     Top5 t;
-    float gate_use = A.g.gate1_d2;                      // phase-1 gate (dense map)
-    bool can_search = A.g.gate1_d2 < A.g.gate_d2, is_seeded = false, skip = false;
+    const bool dense = A.g.gate1_d2 < A.g.gate_d2;     // phase-1 gate active (cell edge = its radius)
+    float gate_use = A.g.gate1_d2;
+    bool can_search = dense, is_seeded = false, skip = false;
+#ifdef S2M_PRESET_SEEDS
+    float sd[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    int sp[5] = {0, 0, 0, 0, 0};
+#endif
     if (s_iter > 0) {
       // Seeded search: the five neighbours of the previous iteration are real map points, so their
       // largest distance to the moved query bounds the true 5th-neighbour distance.  Searching inside
@@ -962,34 +1033,65 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
           can_search = true;
           is_seeded = true;
           ++seeded;
-#ifndef S2M_NO_SEED_INIT
-          // The five seeds enter the list up front, all lanes together.  In a late iteration they ARE the answer and the
-          // walk then inserts nothing: the insertion network otherwise runs ~30 times per warp at 5 of 32 lanes (25 % of
-          // the kernel's instructions, profiles/r02_ncu_source_hotspots_*).  Measured: -8 us per seeded launch.
-          t.init(bound);
-          t.offer(d0, p0); t.offer(d1, p1); t.offer(d2, p2); t.offer(d3, p3); t.offer(d4, p4);
+#ifdef S2M_PRESET_SEEDS
+          sd[0] = d0; sd[1] = d1; sd[2] = d2; sd[3] = d3; sd[4] = d4;
+          sp[0] = p0; sp[1] = p1; sp[2] = p2; sp[3] = p3; sp[4] = p4;
 #endif
         }
       }
     }
+    // How the seeded points of this warp search (all three are exact; the choice only moves time):
+    //   the last pose step was small for most of them -> collect, then select (grid_knn5_collect): 58 vs 70 us per launch;
+    //   otherwise -> the insertion walk that tightens its bound as it goes (after a large step the seeds' bound is loose:
+    //   collecting then costs 130 us instead of 77).
+    bool use_collect = false;
+#ifndef S2M_NO_COLLECT
+    if (s_iter > 0 && dense) {
+      const float range = sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z);
+      const unsigned act = __activemask();
+      const unsigned ms = __ballot_sync(act, is_seeded);
+      const unsigned mt = __ballot_sync(act, is_seeded && step_t + step_r * range < S2M_COLLECT_MOVE);
+      use_collect = 4 * __popc(mt) >= 3 * __popc(ms);
+    }
+#endif
+    bool preset = false;
+#ifdef S2M_PRESET_SEEDS
+    // A/B: the five seeds enter the list up front and the walk skips them when it meets them (grid_knn5<true>).  Measured
+    // on this kernel: -2 us on a late iteration (where collecting wins by 12), +8 us on the iteration after a large step.
+    if (is_seeded && !use_collect) {
+      t.init(gate_use);
+      t.offer(sd[0], sp[0]); t.offer(sd[1], sp[1]); t.offer(sd[2], sp[2]); t.offer(sd[3], sp[3]); t.offer(sd[4], sp[4]);
+      preset = true;
+    }
+#endif
     if (skip) {
       t.init(A.g.gate_d2);  // "not found": flag false, no seeds for the next iteration, marker kept
       need2 = false;
     } else if (can_search) {
-#ifndef S2M_NO_BOX9
-      // dense map: the row-by-row walk (x ranges tightened as the bound shrinks) executes fewer instructions
-      // and the kernel is issue bound; sparse map (1 m cells, few points per row): the search is latency
-      // bound and the all-rows-at-once variant wins
-      const bool sparse = !(A.g.gate1_d2 < A.g.gate_d2);
-#ifndef S2M_NO_SEED_INIT
-      if (is_seeded) {
-        if (!sparse || !grid_knn5_box9<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
-          grid_knn5<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
-      } else
-#endif
-      if (!sparse || !grid_knn5_box9(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
-#endif
-        grid_knn5(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+      bool searched = false;
+      if (is_seeded && use_collect) {
+        const int cnt = grid_knn5_collect<S2M_THREADS>(sel, A.g, gate_use, A.map_sorted, A.cell_start, slist);
+        if (cnt <= S2M_COLLECT_CAP) {  // else: the list overflowed, the insertion walk below repeats the search
+          t.init(gate_use);
+          for (int j = 0; j < cnt; ++j) {
+            const u64 key = slist[j * S2M_THREADS];
+            t.offer(__uint_as_float((unsigned)(key >> 32)), (int)(unsigned)(key & 0xffffffffull));
+          }
+          searched = true;
+        }
+      }
+      if (!searched) {
+        // dense map: the row-by-row walk (x ranges tightened as the bound shrinks) executes fewer instructions
+        // and the kernel is issue bound; sparse map (1 m cells, few points per row): the search is latency
+        // bound and the all-rows-at-once variant wins
+        if (preset) {
+          if (dense || !grid_knn5_box9<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
+            grid_knn5<true>(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+        } else {
+          if (dense || !grid_knn5_box9(sel, A.g, gate_use, A.map_sorted, A.cell_start, t))
+            grid_knn5(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
+        }
+      }
       need2 = !is_seeded && !(t.d(t.k4) < A.g.gate1_d2);
     } else {
       need2 = true;
@@ -1002,6 +1104,8 @@ s2m_main_kernel(const S2mArgs A) {
   __shared__ float sT[12];
   __shared__ LmTrig sTrig;
   __shared__ float rows[S2M_THREADS][8];  // 6 Jacobian entries, rhs, accepted flag
+  __shared__ u64 s_list[S2M_COLLECT_CAP][S2M_THREADS];  // candidates inside the bound (grid_knn5_collect), slot-major
+  __shared__ float s_step[2];
   __shared__ double red[S2M_THREADS / 32][S2M_SUMS];
   __shared__ int s_ties, s_wfail[S2M_THREADS / 32], s_iter, s_seeded;
   __shared__ bool s_last;
@@ -1019,6 +1123,7 @@ s2m_main_kernel(const S2mArgs A) {
     s_seeded = 0;
   }
   if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
+  if (tid == 96) { s_step[0] = A.st->delta_t * 0.01f; s_step[1] = A.st->delta_r * 0.01745329f; }  // last step: metres, radians
   __syncthreads();
   if (A.mode == 0 && s_done0) return;
 
@@ -1027,7 +1132,7 @@ s2m_main_kernel(const S2mArgs A) {
   float rhs = 0.f;
   bool flag = false, tie = false, need2 = false;
   int seeded = 0;
-  if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded);
+  if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded, &s_list[0][tid], s_step[0], s_step[1]);
   // leftover indices, in thread order, into this block's segment
   const unsigned fm = __ballot_sync(0xffffffffu, need2);
   if (lane == 0) s_wfail[warp] = __popc(fm);
@@ -1123,6 +1228,8 @@ s2m_main_pw_kernel(const S2mArgs A) {
   __shared__ float sT[12];
   __shared__ LmTrig sTrig;
   __shared__ float rows[S2M_THREADS][8];
+  __shared__ u64 s_list[S2M_COLLECT_CAP][S2M_THREADS];
+  __shared__ float s_step[2];
   __shared__ int s_iter, s_done0;
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1133,6 +1240,7 @@ s2m_main_pw_kernel(const S2mArgs A) {
     sTrig.cry = A.st->trig[3]; sTrig.srz = A.st->trig[4]; sTrig.crz = A.st->trig[5];
   }
   if (tid == 64) { s_done0 = A.st->done; s_iter = A.mode == 0 ? A.st->iter : 0; }
+  if (tid == 96) { s_step[0] = A.st->delta_t * 0.01f; s_step[1] = A.st->delta_r * 0.01745329f; }  // last step: metres, radians
   __syncthreads();
   if (A.mode == 0 && s_done0) return;
   const int nchunks = A.main_blocks;
@@ -1147,7 +1255,7 @@ s2m_main_pw_kernel(const S2mArgs A) {
     float rhs = 0.f;
     bool flag = false, tie = false, need2 = false;
     int seeded = 0;
-    if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded);
+    if (i < A.nq) main_point(A, sT, sTrig, s_iter, i, row, rhs, flag, tie, need2, seeded, &s_list[0][tid], s_step[0], s_step[1]);
     const unsigned fm = __ballot_sync(0xffffffffu, need2);
     if (need2) A.fail_seg[(size_t)c * 32 + __popc(fm & ((1u << lane) - 1u))] = i;
     if (lane == 0) A.block_nfail[c] = __popc(fm);
