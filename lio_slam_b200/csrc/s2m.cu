@@ -1371,6 +1371,10 @@ s2m_left_kernel(const S2mArgs A) {
   // sparse map (no phase-1 gate): on iteration 0 (and in mode 1) the main kernel did not run at all
   const bool all_points = !(A.g.gate1_d2 < A.g.gate_d2) && (A.mode == 1 || s_iter0 == 0);
   const int total = all_points ? A.nq : s_total0;
+  if (A.mode == 0 && blockIdx.x == 0 && tid == 0 && s_iter0 < LIOGPU_MAX_ITER) {  // statistics
+    A.st->left_hist[s_iter0] = total;
+    A.st->leftovers = total;
+  }
   const int warps_per_grid = gridDim.x * (LEFT_THREADS / 32);
   // points per warp: as few as possible (each point is a serial chain of dependent look-ups, so spreading
   // them over all resident warps hides that latency), up to 32 when there are more points than warps
@@ -1884,6 +1888,7 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
     info->kernel_launches = (int)(c->launches - launches_before);
     info->main_kernel_ms = prof_main_ms; info->left_kernel_ms = prof_left_ms;
     info->main_kernel_launches = prof_main_n; info->left_kernel_launches = prof_left_n;
+    for (int it = 0; it < LIOGPU_MAX_ITER; ++it) info->leftover_hist[it] = h->left_hist[it];
   }
   if (h->cert_mismatch) { c->err = "internal: eigen certificate contradicted by the exact computation"; return LIOGPU_E_INVALID; }
   return LIOGPU_OK;
