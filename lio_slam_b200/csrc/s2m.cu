@@ -187,6 +187,10 @@ __device__ __forceinline__ void grid_knn5(const float4 q, const GridParams& g, c
 // where it runs ~30 times per warp at 5 of 32 lanes; the five are selected afterwards with all lanes in step.  The bound
 // is not tightened during the walk (nothing to gain when it is tight from the start).  Returns the number of candidates
 // inside the bound; more than S2M_COLLECT_CAP means the list overflowed (the caller repeats with the insertion walk).
+#ifndef S2M_GATE1_WIDEN_CFG
+#define S2M_GATE1_WIDEN_CFG 1.0f
+#endif
+constexpr float S2M_GATE1_WIDEN = S2M_GATE1_WIDEN_CFG;  // (radius factor)^2 of the unseeded search in the main kernel
 #ifndef S2M_COLLECT_CAP_CFG
 #define S2M_COLLECT_CAP_CFG 16
 #endif
@@ -1002,7 +1006,11 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
     const float4 sel = apply_T(sT, ori);
     Top5 t;
     const bool dense = A.g.gate1_d2 < A.g.gate_d2;     // phase-1 gate active (cell edge = its radius)
-    float gate_use = A.g.gate1_d2;
+    // An unseeded point searches a somewhat wider ball than the phase-1 radius: the walk is centre-out and pruned against the
+    // running 5th distance, so only the few points without five neighbours inside the phase-1 radius pay for it, and most
+    // of them are settled here instead of by a warp-cooperative full-gate search in the leftover kernel.
+    float gate_use = fminf(A.g.gate1_d2 * S2M_GATE1_WIDEN, A.g.gate_d2);
+    const float gate1_use = gate_use;
     bool can_search = dense, is_seeded = false, skip = false;
 #ifdef S2M_PRESET_SEEDS
     float sd[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1092,7 +1100,7 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
             grid_knn5(sel, A.g, gate_use, A.map_sorted, A.cell_start, t);
         }
       }
-      need2 = !is_seeded && !(t.d(t.k4) < A.g.gate1_d2);
+      need2 = !is_seeded && !(t.d(t.k4) < gate1_use);
     } else {
       need2 = true;
     }
@@ -1115,6 +1123,8 @@ s2m_main_kernel(const S2mArgs A) {
   // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream
   // was still in its single-block tail; nothing it wrote may be read before this returns.
   cudaGridDependencySynchronize();
+  // a launch enqueued beyond the loop's last iteration: every thread sees the flag itself and leaves at once
+  if (A.mode == 0 && __ldcg(&A.st->done)) return;
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];  // updatePointAssociateToMap (:1613-1616)
   if (tid == 32) {
     sTrig.srx = A.st->trig[0]; sTrig.crx = A.st->trig[1]; sTrig.sry = A.st->trig[2];
@@ -1331,6 +1341,7 @@ s2m_left_kernel(const S2mArgs A) {
   __shared__ int s_done0, s_iter0, s_total0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cudaGridDependencySynchronize();  // see s2m_main_kernel
+  if (A.mode == 0 && __ldcg(&A.st->done)) return;  // enqueued beyond the last iteration (before the offset scan below)
   // every global value the block needs is requested in one go (one L2 round trip instead of four)
   if (tid < 12) sT[tid] = A.T_override ? A.T_override[tid] : A.st->T[tid];
   if (tid == 32) {
@@ -1817,6 +1828,9 @@ static int scan2map_legacy_dev(Ctx* c, const float4* scan4, int n, float pose_io
   // (a launch that finds `done` set exits at once), then the state block is read back — the same single
   // read-back a converged registration needs anyway.  Only scans that need more than S2M_CHUNK iterations
   // pay a second round trip.
+  // (Sizing the first chunk from the previous registration's iteration count — 2.8 on the 64-beam sequences, where a
+  // chunk of 5 spends two launch pairs of ~5 us per scan on nothing — was tried: a misprediction costs a second host
+  // round trip, and the batch-mapping throughput did not improve beyond its run-to-run noise.)
   const int S2M_CHUNK = 5;
   const bool pw = use_pw_main(c);
   const int pw_grid = pw_grid_size(c, main_blocks);
