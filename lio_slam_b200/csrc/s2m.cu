@@ -933,6 +933,7 @@ struct S2mArgs {
   int mode;
   int main_blocks;         // partial rows of the main phase
   int seg_blocks;          // leftover segments (= main_blocks except for the split search kernel's smaller blocks)
+  float collect_move;      // metres: a warp collects when most of its seeded points moved less than this (see main_point)
   int seg_stride;          // slots per segment of fail_seg (S2M_THREADS, or 32 for the persistent-warp main kernel)
   unsigned* queue;         // chunk queue head of the persistent-warp main kernel
   int* prev_nn;            // [5][nq] neighbours found by the previous iteration (-1: none), SoA
@@ -1058,7 +1059,7 @@ __device__ __forceinline__ void main_point(const S2mArgs& A, const float* sT, co
       const float range = sqrtf(ori.x * ori.x + ori.y * ori.y + ori.z * ori.z);
       const unsigned act = __activemask();
       const unsigned ms = __ballot_sync(act, is_seeded);
-      const unsigned mt = __ballot_sync(act, is_seeded && step_t + step_r * range < S2M_COLLECT_MOVE);
+      const unsigned mt = __ballot_sync(act, is_seeded && step_t + step_r * range < A.collect_move);
       use_collect = 4 * __popc(mt) >= 3 * __popc(ms);
     }
 #endif
@@ -1623,6 +1624,10 @@ static int prepare_args(Ctx* c, const float4* scan4, int n, S2mArgs& A, int& mai
   A.fail_seg = fb;
   A.seg_stride = seg;
   A.seg_blocks = seg_blocks;
+  // LIOGPU_COLLECT_MOVE (metres) overrides the threshold of the collecting walk: 0 = never collect, a huge value = every
+  // seeded iteration collects (tests/test_gpu_variants.py uses both to exercise the list-overflow fallback)
+  static const float collect_move = [] { const char* e = getenv("LIOGPU_COLLECT_MOVE"); return e ? (float)atof(e) : S2M_COLLECT_MOVE; }();
+  A.collect_move = collect_move;
   A.queue = c->block_counter.as<unsigned>() + 4;
   A.fail_off = fb + (size_t)seg_blocks * seg;
   A.block_nfail = A.fail_off + seg_blocks + 1;

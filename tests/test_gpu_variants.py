@@ -1,5 +1,5 @@
-"""The A/B variants of the main kernel of the two-kernel LM loop (LIOGPU_MAIN = pw | wc | wc1 | split, s2m.cu) must not
-change a single bit: the variant is chosen per process by an environment variable, so every variant runs the same
+"""The A/B variants of the main kernel of the two-kernel LM loop (LIOGPU_MAIN = pw | wc | wc1 | split, s2m.cu) and the two
+extremes of the collecting walk's threshold (LIOGPU_COLLECT_MOVE) must not change a single bit: the variant is chosen per process by an environment variable, so every variant runs the same
 dense-map registration in a child process and its outputs are held against the default kernel's, run here —
   * one surfOptimization pass (mode 1): neighbour indices, squared distances, coefficients, flags, tie bits;
   * the whole loop: pose history, nsel history, JtJ / Jtr of the last iteration, tie count, matP, isDegenerate.
@@ -40,7 +40,12 @@ def run_variant(variant, tmpdir):
     out = os.path.join(tmpdir, f"{variant or 'default'}.npz")
     env = dict(os.environ)
     env.pop("LIOGPU_MAIN", None)
-    if variant:
+    env.pop("LIOGPU_COLLECT_MOVE", None)
+    if variant == "collect_always":      # every seeded iteration collects: loose bounds overflow the lists -> fallback walk
+        env["LIOGPU_COLLECT_MOVE"] = "1e9"
+    elif variant == "collect_never":     # the insertion walk everywhere
+        env["LIOGPU_COLLECT_MOVE"] = "0"
+    elif variant:
         env["LIOGPU_MAIN"] = variant
     r = subprocess.run([sys.executable, "-c", CHILD.format(root=ROOT, out=out)], env=env, capture_output=True, text=True,
                        timeout=600)
@@ -54,7 +59,7 @@ def reference_run():
         yield run_variant("", d)
 
 
-@pytest.mark.parametrize("variant", ["pw", "wc", "wc1", "split"])
+@pytest.mark.parametrize("variant", ["pw", "wc", "wc1", "split", "collect_always", "collect_never"])
 def test_main_kernel_variant_is_bit_identical_to_the_default(reference_run, variant):
     with tempfile.TemporaryDirectory() as d:
         got = run_variant(variant, d)
