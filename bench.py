@@ -418,8 +418,8 @@ def bench_cfg5(torch, dist, rank, world_size, local_rank, n_seq=8, n_scans=200, 
         # mapping workers (one liogpu context + host thread each) exist before the job starts, like a mapping
         # service's pool; every worker replays its share of the sequences one after another on its own context
         workers = [replay.Worker(prm) for _ in range(conc)]
-        for wk in workers:   # warm-up: buffers find their size, kernels are loaded, clocks ramp (not timed)
-            wk.replay(seqs[which[0]], count=min(30, n_scans))
+        for wk in workers:   # warm-up: buffers and keyframe slabs find their size, kernels are loaded, clocks ramp (not timed)
+            wk.replay(seqs[which[0]], count=n_scans)
         results = {}
 
         def run(wk, mine):

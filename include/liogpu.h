@@ -160,7 +160,9 @@ int liogpu_voxel_downsample(liogpu_ctx* ctx, const void* xyzi, int n, int stride
 
 /* surfCloudKeyFrames.push_back (MO:2142): keep a lidar-frame keyframe cloud resident on the GPU. */
 int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int stride);
-/* drop all keyframes (node reset). */
+/* drop all keyframes (node reset).  The device slabs that held them stay with the context and are filled again by the
+ * next keyframes (freeing / allocating device memory would synchronise every other context on the GPU); they are
+ * released by liogpu_destroy. */
 int liogpu_keyframe_clear(liogpu_ctx* ctx);
 int liogpu_keyframe_count(const liogpu_ctx* ctx);
 

@@ -420,15 +420,21 @@ int liogpu_keyframe_put(liogpu_ctx* ctx, int id, const void* xyzi, int n, int st
       fresh = old->second.first;  // overwrite in place (same id, fits): nothing can fail between here and the copy
     } else {
       constexpr size_t SLAB = 32u << 20;
-      if (c->kf_slabs.empty() || c->kf_slab_used + need > c->kf_slab_size) {
+      // current slab, else the next one kept from before liogpu_keyframe_clear, else a new one (cudaMalloc synchronises the
+      // whole device, i.e. every other context on it: slabs are therefore never given back before the context is destroyed)
+      for (;;) {
+        if (c->kf_slab_cur < c->kf_slabs.size() && c->kf_slab_used + need <= c->kf_slab_sizes[c->kf_slab_cur]) break;
+        if (c->kf_slab_cur + 1 < c->kf_slabs.size()) { ++c->kf_slab_cur; c->kf_slab_used = 0; continue; }
         const size_t sz = need > SLAB ? need : SLAB;
         void* slab = nullptr;
         LIOGPU_CUDA_OK(c, cudaMalloc(&slab, sz));
         c->kf_slabs.push_back(slab);
+        c->kf_slab_sizes.push_back(sz);
+        c->kf_slab_cur = c->kf_slabs.size() - 1;
         c->kf_slab_used = 0;
-        c->kf_slab_size = sz;
+        break;
       }
-      fresh.p = (char*)c->kf_slabs.back() + c->kf_slab_used;
+      fresh.p = (char*)c->kf_slabs[c->kf_slab_cur] + c->kf_slab_used;
       fresh.cap = need;
       fresh.pooled = true;
       c->kf_slab_used += need;  // an overwritten, smaller keyframe's bytes stay in their slab until liogpu_keyframe_clear
@@ -454,9 +460,8 @@ int liogpu_keyframe_clear(liogpu_ctx* ctx) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->keyframes) kv.second.first.release();
   c->keyframes.clear();
-  for (void* slab : c->kf_slabs) cudaFree(slab);
-  c->kf_slabs.clear();
-  c->kf_slab_used = c->kf_slab_size = 0;
+  c->kf_slab_cur = 0;  // the slabs stay with the context and are filled again from the first one (no cudaFree / cudaMalloc:
+  c->kf_slab_used = 0; // both synchronise the device); liogpu_destroy releases them
   return LIOGPU_OK;
 }
 

@@ -148,7 +148,8 @@ struct Ctx {
   // no cudaMalloc (which would synchronise the whole device, i.e. every other context on it)
   std::map<int, std::pair<DevBuf, int>> keyframes;
   std::vector<void*> kf_slabs;
-  size_t kf_slab_used = 0, kf_slab_size = 0;
+  std::vector<size_t> kf_slab_sizes;
+  size_t kf_slab_cur = 0, kf_slab_used = 0;  // slab being filled, bytes used in it
   // deskew
   DevBuf imu_tab, dsk_flags, dsk_scan;
   // publishLocalMap (localmap.cu): crop / outlier-filter scratch and the filter's own neighbour grid
