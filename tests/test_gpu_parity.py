@@ -280,6 +280,43 @@ def test_build_local_map_bitexact(gpu, oracle, world):
         gpu.build_local_map([99], np.array(poses)[:1], 0.5)
 
 
+def test_keyframe_slabs_are_reused_after_clear(oracle, world):
+    """liogpu_keyframe_clear keeps the device slabs (no cudaFree / cudaMalloc between sequences): keyframes put after a
+    clear land in the old slabs — several slabs' worth, other sizes, other ids — and the map built from them is the oracle's."""
+    from lio_slam_b200.liogpu import LioGpu, LioGpuError
+    g = LioGpu()
+    try:
+        rng = np.random.default_rng(5)
+        big = (rng.standard_normal((1_200_000, 4)) * np.array([30, 30, 3, 1])).astype(np.float32)   # 19 MB each: 2 per slab at most
+        for k in range(4):                       # generation 1: fills three 32 MiB slabs
+            g.keyframe_put(k, big[: 1_200_000 - 1000 * k])
+        assert g.keyframe_count() == 4
+        g.keyframe_clear()
+        assert g.keyframe_count() == 0
+        with pytest.raises(LioGpuError):         # nothing of generation 1 is reachable any more
+            g.build_local_map([0], np.zeros((1, 6), np.float32), 0.5)
+        clouds, poses = [], []
+        for k in range(5):                       # generation 2: small clouds first, then a large one crossing into the next slab
+            p = synth.path_pose(-0.5 * k)
+            sc = synth.make_scan(world, p, 16, seed=300 + k, cols=450)
+            clouds.append(oracle.voxel_grid(synth.to_packed(sc), 0.4)[0]); poses.append(p.astype(np.float32))
+        for k, c in enumerate(clouds):
+            g.keyframe_put(100 + k, c)
+        g.keyframe_put(200, big)                 # does not fit behind the small ones in slab 0 -> slab 1 (kept from generation 1)
+        g.keyframe_put(100, clouds[0])           # overwrite in place
+        want, _ = oracle.build_local_map(clouds, np.array(poses), 0.5, threads=4)
+        got, st = g.build_local_map([100 + k for k in range(5)], np.array(poses), 0.5)
+        assert st == 0
+        assert_biteq(got, want, "map from keyframes stored in reused slabs")
+        g.keyframe_clear()
+        g.keyframe_put(7, clouds[2])             # generation 3 starts at the first slab again
+        got3, _ = g.build_local_map([7], np.array(poses)[2:3], 0.5)
+        want3, _ = oracle.build_local_map([clouds[2]], np.array(poses)[2:3], 0.5, threads=2)
+        assert_biteq(got3, want3)
+    finally:
+        g.close()
+
+
 # ---------------------------------------------------------------- a1 deskew
 @pytest.mark.parametrize("cfg", [dict(), dict(downsample_rate=2, point_filter_num=3), dict(point_filter_num=5, lidar_max_range=40.0)])
 def test_deskew_parity(oracle, world, cfg):
