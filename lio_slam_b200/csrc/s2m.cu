@@ -7,21 +7,26 @@
 //     2. exact 5-NN on the sorted grid (grid.cu): rows of x-adjacent cells are contiguous ranges of map_sorted;
 //        rows are visited centre-out and pruned against the running 5th-best distance; distances are FLANN
 //        L2_Simple in f32 without FMA; ties -> lower map index.  Iteration 0 searches inside a small phase-1
-//        gate; iterations >= 1 inside the bound given by the previous iteration's neighbours (seeded search);
-//        points with too few map points around are skipped by the exact "hopeless" rule
+//        gate; iterations >= 1 inside the bound given by the previous iteration's neighbours (seeded search) —
+//        as the insertion walk after a large pose step, as collect-then-select (grid_knn5_collect) after a small
+//        one; points with too few map points around are skipped by the exact "hopeless" rule
 //     3. 5x3 column-pivoted Householder plane fit, validity, weight s, coefficient (:1633-1684)
 //     4. Jacobian row (:1760-1778) staged in shared memory; the block reduces the 27 sums of A^T A (upper
 //        triangle) and A^T b in FP64 (cv::gemm accumulates f32 products in double)
 //     5. points phase 1 could not settle go to a per-block segment of the leftover list
-//   s2m_left_kernel   warp-cooperative full-gate search of the leftovers (one per warp), fold of all partial
-//     sums in a fixed order, and — in the last block to finish — the 6x6 tail of LMOptimization
+//   s2m_left_kernel   offsets of the leftover segments (parallel scan in every block), warp-cooperative full-gate
+//     search of the leftovers (one per warp), fold of all partial sums in a fixed order, and — in the last block
+//     to finish — the 6x6 tail of LMOptimization
 //     (lm_finalize_warp): QR solve, degeneracy decision / matP on iteration 0, projection, pose update,
 //     convergence test (:1784-1835), next iteration's transform
 //   lm_matp_kernel    iteration 0's Jacobi eigen-decomposition + matP on a second stream when a rigorous
 //     certificate has already decided isDegenerate = false
+//   A/B variants of the main kernel (LIOGPU_MAIN, bit-identical results, all measured slower: DESIGN.md §4):
+//     s2m_main_pw_kernel (persistent warps), s2m_wc.cuh (warp-cooperative candidate evaluation), s2m_split.cuh
+//     (search in one wave + fit kernel); s2m_fused.cuh is the whole loop as one cooperative launch (params.s2m_path = 2)
 //
 // The pose, matP, isDegenerate and the iteration counter stay in HBM (LmDevState); the host enqueues a chunk of
-// iterations back to back and reads the 1.8 KB state once — a launch that finds `done` set returns immediately.
+// iterations back to back and reads the 2.5 KB state once — a launch that finds `done` set returns immediately.
 // Compaction (:1689-1700) is unnecessary: rejected points contribute exact zeros to the FP64 sums.
 //
 // Algorithmic HBM bytes per launch: 16 B query + 5 x 16 B neighbours = 96 B per sweep point.
@@ -908,7 +913,8 @@ __device__ __noinline__ void lm_finalize_warp(LmDevState* st, const double* sums
 //                    row, FP64 block reduction -> partials[block].  A point whose 5 neighbours are not all
 //                    inside the phase-1 radius is NOT searched further here: its index goes to the block's
 //                    segment of `fail_seg` (deterministic order) so no warp ever waits for a straggler.
-//                    The last block to finish turns the per-block counts into one dense list.
+//                    The leftover kernel turns the per-block counts into segment offsets (only when that table
+//                    exceeds its shared memory does the main kernel's last block still do it).
 //   s2m_left_kernel  the leftover points (about 2 % on a dense map, all of them on a sparse one), 32 per
 //                    warp: warp-cooperative full-gate search per point, then the plane fit lane-parallel.
 //                    Its blocks also fold the main kernel's partials; the last block adds everything in a
