@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--workloads", default="cfg3,cfg1")
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--variants", default="fused,fused_nocert,two_kernel")
+    ap.add_argument("--order", default="sweep", help="sweep (ring-major, as the sensor delivers it) | tileRxC: the sweep is "
+                    "re-ordered on the host into tiles of R rings x C columns (R*C = 256 = one thread block) — an experiment on "
+                    "the locality of the candidate loads, organised sweeps only")
     args = ap.parse_args()
     import torch
     import bench
@@ -31,6 +34,14 @@ def main():
     for name in args.workloads.split(","):
         w = bench.WORKLOADS[name]
         map4, scans, guesses = bench.make_workload(name, 0, 4)
+        if args.order.startswith("tile"):
+            R, Cc = (int(x) for x in args.order[4:].split("x"))
+            beams, cols = w["beams"], w["cols"]
+            if all(sc.shape[0] == beams * cols for sc in scans) and beams % R == 0 and cols % Cc == 0:
+                idx = np.arange(beams * cols).reshape(beams // R, R, cols // Cc, Cc).transpose(0, 2, 1, 3).reshape(-1)
+                scans = [np.ascontiguousarray(sc[idx]) for sc in scans]
+            else:
+                print(f"[{name}] not an organised {beams} x {cols} sweep: order left as is", file=sys.stderr)
         dev = [torch.from_numpy(s).cuda() for s in scans]
         ref_hist = None
         for var in args.variants.split(","):
@@ -71,7 +82,7 @@ def main():
                 ref_hist = hist
             same = all(a[0] == b[0] and a[1] == b[1] for a, b in zip(hist, ref_hist))
             pose_eq = all(a[2] == b[2] for a, b in zip(hist, ref_hist))
-            print(json.dumps(dict(workload=name, variant=var, lib=os.environ.get("LIOGPU_LIB", "default"), n_query=int(scans[0].shape[0]), same_iterations_and_nsel=same,
+            print(json.dumps(dict(workload=name, variant=var, order=args.order, lib=os.environ.get("LIOGPU_LIB", "default"), n_query=int(scans[0].shape[0]), same_iterations_and_nsel=same,
                                   poses_bit_equal_to_first_variant=pose_eq, **res)), flush=True)
             assert same, "variants disagree on iteration counts / nsel history"
 
