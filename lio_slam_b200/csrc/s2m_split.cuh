@@ -10,6 +10,10 @@
 //   s2m_fit_kernel     one thread per point, fully convergent: neighbour gather, 5x3 plane fit, Jacobian row, FP64 block
 //                      sums into the same partial rows s2m_main_kernel writes.
 //
+// STATUS: A/B variant (LIOGPU_MAIN=split), parity-green (tests/test_gpu_variants.py), MEASURED NOT FASTER: search + fit
+// 70-79 us per iteration on config 3 (s2m_main_kernel: 72 before, 68 after the collecting walk) — the one-wave residency
+// did not shorten the search, and the second launch + re-gather of the neighbours cost what it saved.
+//
 // The leftover kernel follows unchanged.  Results are bit-identical to s2m_main_kernel (same per-point arithmetic, same
 // assignment of points to partial rows).
 #pragma once

@@ -1,7 +1,13 @@
 // s2m_wc.cuh — s2m_main_wc_kernel: the search of surfOptimization (mapOptmization.cpp:1622-1641) with the candidate
 // evaluation done WARP-COOPERATIVELY at full lane occupancy.  Included by s2m.cu (same translation unit).
 //
-// Why: s2m_main_kernel gives every sweep point a thread that walks its own rows of grid cells; ncu shows that kernel
+// STATUS: A/B variant (LIOGPU_MAIN=wc), parity-green (tests/test_gpu_variants.py), MEASURED SLOWER than s2m_main_kernel on
+// config 3: 100-108 us on a late iteration, 230-290 us on iterations 0-1 (68 us average for the default).  ncu
+// (profiles/r02_ncu_full_s2m_main_wc_kernel.csv): 26 of 32 lanes active as intended, but the flat candidate list costs ~60
+// instructions per candidate (segment tracking, owner look-ups, shared-memory atomics), so a launch executes 33-75 M warp
+// instructions, no fewer than the per-thread walk's 36-40 M, at issue rate 0.38 and 3 CTAs per SM.
+//
+// Why it was built: s2m_main_kernel gives every sweep point a thread that walks its own rows of grid cells; ncu shows that kernel
 // issue bound with 17 of 32 lanes active per instruction — the lanes of a warp visit different numbers of rows and
 // candidates, and the top-5 insertion runs at 6 of 32 lanes.  Here the irregular part is flattened:
 //
